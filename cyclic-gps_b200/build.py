@@ -1,0 +1,89 @@
+"""Build libcrb200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+    python cyclic-gps_b200/build.py [--force] [-j N]
+
+The template instantiations are split over 16 translation units (dtype x ell range) and
+compiled in parallel; objects are cached under cyclic-gps_b200/build/ keyed by a hash of
+the sources and flags.  The resulting .so sits next to this file (git-ignored, but it travels
+to the GPU box with the repo snapshot)."""
+import argparse
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libcrb200.so")
+BUILD = os.path.join(HERE, "build")
+RANGES = [(1, 4), (5, 8), (9, 12), (13, 16), (17, 20), (21, 24), (25, 28), (29, 32)]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+
+
+def _nvcc():
+    cand = os.environ.get("NVCC")
+    if cand:
+        return cand
+    if os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return "/usr/local/cuda/bin/nvcc"
+    return "nvcc"
+
+
+def source_hash():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "crb200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS[:6]).encode())
+    return h.hexdigest()[:16]
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def is_current():
+    stamp = os.path.join(BUILD, "stamp")
+    return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash()
+
+
+def build(force=False, jobs=None, verbose=False):
+    if not force and is_current():
+        return OUT
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    units = []
+    for tn, ty in (("f32", "float"), ("f64", "double")):
+        for lo, hi in RANGES:
+            obj = os.path.join(BUILD, f"inst_{tn}_{lo}_{hi}.o")
+            units.append((obj, [nvcc] + NVCC_FLAGS + [f"-DCRB_T={ty}", f"-DCRB_TN={tn}", f"-DCRB_LO={lo}", f"-DCRB_HI={hi}",
+                                                       "-c", os.path.join(CSRC, "cr_inst.cu"), "-o", obj]))
+    abi_obj = os.path.join(BUILD, "cr_abi.o")
+    units.append((abi_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_abi.cu"), "-o", abi_obj]))
+    jobs = jobs or min(len(units), os.cpu_count() or 4)
+    # longest units (large ell) first
+    units.sort(key=lambda u: -int(u[0].rsplit("_", 1)[-1].split(".")[0]) if "inst_" in u[0] else 0)
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        for out in ex.map(lambda u: _run(u[1]), units):
+            if verbose and out.strip():
+                print(out)
+    _run([nvcc, "-shared", "-o", OUT] + [u[0] for u in units] + ["-lcudart"])
+    with open(os.path.join(BUILD, "stamp"), "w") as fh:
+        fh.write(source_hash())
+    return OUT
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-j", type=int, default=None)
+    ap.add_argument("-v", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, jobs=a.j, verbose=a.v))

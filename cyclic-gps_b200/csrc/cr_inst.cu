@@ -1,0 +1,44 @@
+// Instantiation unit: compiled once per (dtype, ell range) so the template expansions build
+// in parallel.  -DCRB_T=float|double -DCRB_TN=f32|f64 -DCRB_LO=.. -DCRB_HI=..
+#include "cr_level_fwd.cuh"
+#include "cr_level_bwd.cuh"
+#include "cr_halfsolve.cuh"
+
+#define CRB_CAT_(a, b, c, d) a##_##b##_##c##_##d
+#define CRB_CAT(a, b, c, d) CRB_CAT_(a, b, c, d)
+
+namespace crb200 {
+
+template <int L>
+struct Dispatch {
+  static cudaError_t fwd(int ell, const LevelFwdArgs& a, cudaStream_t s) {
+    if (ell == L) return launch_level_fwd<CRB_T, L>(a, s);
+    return Dispatch<L + 1>::fwd(ell, a, s);
+  }
+  static cudaError_t bwd(int ell, const LevelBwdArgs& a, cudaStream_t s) {
+    if (ell == L) return launch_level_bwd<CRB_T, L>(a, s);
+    return Dispatch<L + 1>::bwd(ell, a, s);
+  }
+  static cudaError_t hs(int ell, const HalfSolveArgs& a, cudaStream_t s) {
+    if (ell == L) return launch_level_halfsolve<CRB_T, L>(a, s);
+    return Dispatch<L + 1>::hs(ell, a, s);
+  }
+  static int fwd_tile(int ell) { return ell == L ? FwdCfg<CRB_T, L>::NG - 1 : Dispatch<L + 1>::fwd_tile(ell); }
+  static int bwd_tile(int ell) { return ell == L ? BwdCfg<CRB_T, L>::NG : Dispatch<L + 1>::bwd_tile(ell); }
+};
+template <>
+struct Dispatch<CRB_HI + 1> {
+  static cudaError_t fwd(int, const LevelFwdArgs&, cudaStream_t) { return cudaErrorInvalidValue; }
+  static cudaError_t bwd(int, const LevelBwdArgs&, cudaStream_t) { return cudaErrorInvalidValue; }
+  static cudaError_t hs(int, const HalfSolveArgs&, cudaStream_t) { return cudaErrorInvalidValue; }
+  static int fwd_tile(int) { return 0; }
+  static int bwd_tile(int) { return 0; }
+};
+
+cudaError_t CRB_CAT(inst_fwd, CRB_TN, CRB_LO, CRB_HI)(int ell, const LevelFwdArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::fwd(ell, a, s); }
+cudaError_t CRB_CAT(inst_bwd, CRB_TN, CRB_LO, CRB_HI)(int ell, const LevelBwdArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::bwd(ell, a, s); }
+cudaError_t CRB_CAT(inst_hs, CRB_TN, CRB_LO, CRB_HI)(int ell, const HalfSolveArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::hs(ell, a, s); }
+int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::fwd_tile(ell); }
+int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::bwd_tile(ell); }
+
+}  // namespace crb200

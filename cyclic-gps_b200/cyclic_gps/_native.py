@@ -1,0 +1,148 @@
+"""ctypes binding of libcrb200.so (include/crb200.h) -- the C-ABI boundary of the CR engine.
+
+The library is built in-tree by ``cyclic-gps_b200/build.py`` and found next to this package.
+There is NO fallback: if the shared object is missing, or there is no CUDA device, the calls
+raise.  Tensors are passed as raw device pointers (``Tensor.data_ptr()``) together with the
+current CUDA stream; torch owns every buffer."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libcrb200.so")
+
+F32, F64 = 0, 1
+OK, EINVAL, EUNSUPPORTED, ECUDA = 0, -1, -2, -3
+
+_vp, _ll, _i = C.c_void_p, C.c_longlong, C.c_int
+
+
+class FwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("m", _i),
+                ("R", _vp), ("O", _vp), ("y", _vp),
+                ("strideR", _ll), ("strideO", _ll), ("stridey", _ll),
+                ("D", _vp), ("F", _vp), ("G", _vp), ("xk", _vp),
+                ("Rn", _vp), ("On", _vp), ("yn", _vp),
+                ("logdet", _vp), ("mahal", _vp), ("info", _vp),
+                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("m", _i),
+                ("D", _vp), ("F", _vp), ("G", _vp), ("xk", _vp),
+                ("Sd_in", _vp), ("So_in", _vp), ("w_in", _vp),
+                ("Sd_out", _vp), ("So_out", _vp), ("w_out", _vp),
+                ("strideSd", _ll), ("strideSo", _ll), ("stridew", _ll),
+                ("gm", _vp), ("gd", _vp), ("grad_mode", _i),
+                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp), ("So_halo_out", _vp)]
+
+
+class HsArgs(C.Structure):
+    _fields_ = [("batch", _i), ("m", _i),
+                ("D", _vp), ("F", _vp), ("G", _vp),
+                ("y", _vp), ("stridey", _ll),
+                ("xk", _vp), ("yn", _vp), ("mahal", _vp)]
+
+
+EXPORTS = ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
+           "crb200_level_bwd", "crb200_level_halfsolve", "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcrb200.so once; raises NativeLibraryMissing when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: build it with `python cyclic-gps_b200/build.py` "
+                "(needs nvcc; there is no CPU or PyTorch fallback for the CR engine)")
+        lib = C.CDLL(LIB_PATH)
+        for name in ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error"):
+            getattr(lib, name).restype = _i
+            getattr(lib, name).argtypes = []
+        lib.crb200_level_fwd.restype = _i
+        lib.crb200_level_fwd.argtypes = [_i, _i, C.POINTER(FwdArgs), _vp]
+        lib.crb200_level_bwd.restype = _i
+        lib.crb200_level_bwd.argtypes = [_i, _i, C.POINTER(BwdArgs), _vp]
+        lib.crb200_level_halfsolve.restype = _i
+        lib.crb200_level_halfsolve.argtypes = [_i, _i, C.POINTER(HsArgs), _vp]
+        for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
+            getattr(lib, name).restype = _i
+            getattr(lib, name).argtypes = [_i, _i]
+        _lib = lib
+    return _lib
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.float64:
+        return F64
+    raise TypeError(f"the CR engine computes in float32 or float64, got {dtype}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("internal error: CPU tensor handed to the native CR library")
+    return t.data_ptr()
+
+
+def _check(rc: int, what: str):
+    if rc == OK:
+        return
+    lib = load()
+    if rc == ECUDA:
+        raise RuntimeError(f"{what}: CUDA launch failed (cudaError {lib.crb200_last_cuda_error()})")
+    if rc == EUNSUPPORTED:
+        raise ValueError(f"{what}: unsupported block size or dtype (1 <= ell <= {lib.crb200_max_ell()}, float32/float64)")
+    raise ValueError(f"{what}: invalid argument (code {rc})")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _fill(struct, fields):
+    for k, v in fields.items():
+        if isinstance(v, torch.Tensor) or v is None:
+            setattr(struct, k, _ptr(v))
+        else:
+            setattr(struct, k, v)
+    return struct
+
+
+def level_fwd(dtype: torch.dtype, ell: int, **fields):
+    a = _fill(FwdArgs(), fields)
+    _check(load().crb200_level_fwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_fwd")
+
+
+def level_bwd(dtype: torch.dtype, ell: int, **fields):
+    a = _fill(BwdArgs(), fields)
+    _check(load().crb200_level_bwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_bwd")
+
+
+def level_halfsolve(dtype: torch.dtype, ell: int, **fields):
+    a = _fill(HsArgs(), fields)
+    _check(load().crb200_level_halfsolve(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_halfsolve")
+
+
+def tile_nodes(dtype: torch.dtype, ell: int):
+    lib = load()
+    return lib.crb200_fwd_tile_nodes(dtype_code(dtype), ell), lib.crb200_bwd_tile_nodes(dtype_code(dtype), ell)

@@ -1,0 +1,364 @@
+"""Drop-in replacement for the reference module ``cyclic_gps/cyclic_reduction.py``: same
+function names, argument names and return structures, computed by hand-written sm_100a
+CUDA kernels (``libcrb200.so``, C ABI in ``include/crb200.h``).
+
+Block cyclic reduction of a symmetric positive-definite block-tridiagonal matrix J with
+diagonal blocks ``Rs:(n,l,l)`` and lower off-diagonal blocks ``Os:(n-1,l,l)``.
+
+Differences from the reference, all additive:
+  * every function also accepts a leading batch axis of independent series
+    (``Rs:(B,n,l,l)``, ``Os:(B,n-1,l,l)``, vectors ``(B,n,l)``); scalars then have shape ``(B,)``;
+  * inputs may live on the CPU or on a CUDA device; results come back on the caller's
+    device (CPU inputs are copied to the current CUDA device and back -- a transfer shim,
+    never a CPU compute path; without a CUDA device the calls raise);
+  * ``mahal_and_det`` and ``det(decompose(...))`` carry a hand-written backward (closed-form
+    gradients from a back-solve + selected inverse) instead of a torch autograd tape;
+  * a non-positive-definite diagonal block raises ``NotPositiveDefiniteError`` (no jitter
+    retry; reference: gpytorch ``psd_safe_cholesky``, cyclic_reduction.py:227,306,429).
+
+``np`` and ``torch`` are re-exported on purpose: the reference's own tests rely on
+``from cyclic_gps.cyclic_reduction import *`` providing them
+(tests/test_cyclic_reduction.py:250-253 of the reference).
+"""
+from math import ceil, floor  # noqa: F401  (names the reference module exports)
+from typing import List, Tuple, Union  # noqa: F401
+
+import numpy as np  # noqa: F401  (re-exported, see module docstring)
+import torch
+
+from . import _engine
+from ._engine import NotPositiveDefiniteError  # noqa: F401
+
+JITTER = None  # reference module attribute (cyclic_reduction.py:13); no jitter is ever added here
+
+
+# ---------------------------------------------------------------------------------------
+# argument plumbing
+# ---------------------------------------------------------------------------------------
+def _check_blocks(Rs, Os):
+    if not (torch.is_tensor(Rs) and torch.is_tensor(Os)):
+        raise TypeError("Rs and Os must be torch tensors")
+    if Rs.dim() not in (3, 4) or Os.dim() != Rs.dim():
+        raise TypeError("Rs must be (n,l,l) or (B,n,l,l) and Os (n-1,l,l) or (B,n-1,l,l)")
+    if Rs.shape[-1] != Rs.shape[-2] or Os.shape[-1] != Os.shape[-2] or Os.shape[-1] != Rs.shape[-1]:
+        raise TypeError("blocks must be square and of one size")
+    if Rs.dtype != Os.dtype:
+        raise TypeError("Rs and Os must share a dtype")
+    # reference: assert num_dblocks == num_offdblocks + 1  (cyclic_reduction.py:223)
+    assert Rs.shape[-3] == Os.shape[-3] + 1, "need exactly one fewer off-diagonal block than diagonal blocks"
+    if Rs.dim() == 4:
+        assert Rs.shape[0] == Os.shape[0], "batch sizes of Rs and Os differ"
+
+
+def _dev(t, dev, dtype=None):
+    """Contiguous copy/view of `t` on the compute device."""
+    if t is None:
+        return None
+    t = t.detach()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(dev, non_blocking=False).contiguous()
+
+
+def _batched(t, batched):
+    return t if batched else t.unsqueeze(0)
+
+
+class CRDecomp(tuple):
+    """``(ms, Ds, Fs, Gs)`` exactly as the reference's ``decompose`` returns it
+    (cyclic_reduction.py:309), plus the device-resident packed factors and the handles
+    needed for the hand-written backward."""
+
+    def __new__(cls, ms, Ds, Fs, Gs, pack=None, Rs=None, Os=None, batched=False, caller_device=None):
+        self = super().__new__(cls, (ms, Ds, Fs, Gs))
+        self._pack = pack
+        self._Rs, self._Os = Rs, Os
+        self._batched = batched
+        self._caller_device = caller_device
+        return self
+
+
+def _pack_of(decomp):
+    """FactorPack + (batched, caller_device) for a CRDecomp or a plain 4-tuple."""
+    if isinstance(decomp, CRDecomp) and decomp._pack is not None:
+        return decomp._pack, decomp._batched, decomp._caller_device
+    ms, Ds, Fs, Gs = decomp
+    dev = _engine.require_cuda()
+    caller = Ds[0].device
+    batched = Ds[0].dim() == 4
+    dtype, ell = Ds[0].dtype, Ds[0].shape[-1]
+    msl = [int(m) for m in ms]
+    B = Ds[0].shape[0] if batched else 1
+    pack = _engine.FactorPack(dtype, ell, B, msl[0], msl)
+    empty = torch.empty((B, 0, ell, ell), dtype=dtype, device=dev)
+    for k, m in enumerate(msl):
+        E, o, g = _engine.counts(m)
+        pack.D.append(_batched(_dev(Ds[k], dev), batched))
+        pack.F.append(_batched(_dev(Fs[k], dev), batched) if o > 0 else empty)
+        pack.G.append(_batched(_dev(Gs[k], dev), batched) if g > 0 else empty)
+        pack.X.append(None)
+    return pack, batched, caller
+
+
+def _vec_levels(pack, ycrr, batched, dev):
+    out = []
+    for k, m in enumerate(pack.ms):
+        v = _batched(_dev(ycrr[k], dev, pack.dtype), batched)
+        E = _engine.counts(m)[0]
+        if v.shape[1] != E or v.shape[2] != pack.ell:
+            raise ValueError(f"level {k}: expected ({E},{pack.ell}) right-hand side, got {tuple(v.shape[1:])}")
+        out.append(v)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# block-bidiagonal helper products (reference :15-200).  Plain tensor algebra on the
+# caller's device: they are tested API surface, not part of the hot path.
+# U has diagonal blocks `diags` (odd node j x even node j) and super-diagonal blocks
+# `offdiags` (odd node j x even node j+1); len(offdiags) == len(diags) means U is o x (o+1).
+# ---------------------------------------------------------------------------------------
+def UU_T(diags, offdiags):
+    """Diagonal and lower off-diagonal blocks of U U^T  (reference :15-37)."""
+    o, g = diags.shape[0], offdiags.shape[0]
+    dd = torch.matmul(diags, diags.transpose(1, 2))
+    gg = torch.matmul(offdiags, offdiags.transpose(1, 2))
+    if g == o:
+        dd = dd + gg
+    else:
+        dd = torch.cat([dd[:g] + gg, dd[g:]], dim=0)
+    low = torch.matmul(diags[1:], offdiags[: max(o - 1, 0)].transpose(1, 2))
+    return dd, low
+
+
+def Ux(diags, offdiags, x):
+    """U @ x  (reference :40-60)."""
+    o, g = diags.shape[0], offdiags.shape[0]
+    out = torch.matmul(diags, x[:o].unsqueeze(-1)).squeeze(-1)
+    gx = torch.matmul(offdiags, x[1:g + 1].unsqueeze(-1)).squeeze(-1)
+    if g == o:
+        return out + gx
+    return torch.cat([out[:g] + gx, out[g:]], dim=0)
+
+
+def U_Tx(diags, offdiags, x):
+    """U.T @ x  (reference :63-87)."""
+    o, g = diags.shape[0], offdiags.shape[0]
+    ft = torch.matmul(diags.transpose(1, 2), x[:o].unsqueeze(-1)).squeeze(-1)
+    gt = torch.matmul(offdiags.transpose(1, 2), x[:g].unsqueeze(-1)).squeeze(-1)
+    if g == o:
+        return torch.cat([ft[:1], ft[1:] + gt[: o - 1], gt[o - 1:]], dim=0)
+    return torch.cat([ft[:1], ft[1:] + gt], dim=0)
+
+
+def SigU(sig_dblocks, sig_offdblocks, u_dblocks, u_offdblocks):
+    """Diagonal and super-diagonal blocks of Sig @ U for symmetric block-tridiagonal Sig
+    given by its diagonal and LOWER off-diagonal blocks  (reference :90-136)."""
+    o, g = u_dblocks.shape[0], u_offdblocks.shape[0]
+    mid = torch.matmul(sig_dblocks, u_dblocks)
+    if o > 1:
+        mid = torch.cat([mid[:1], mid[1:] + torch.matmul(sig_offdblocks, u_offdblocks[: o - 1])], dim=0)
+    hi = torch.matmul(sig_dblocks[:g], u_offdblocks)
+    k = min(g, o - 1)
+    if k > 0:
+        hi = torch.cat([hi[:k] + torch.matmul(sig_offdblocks[:k].transpose(1, 2), u_dblocks[1:k + 1]), hi[k:]], dim=0)
+    return mid, hi
+
+
+def UtV_diags(u_dblocks, u_offdblocks, v_dblocks, v_offdblocks):
+    """Diagonal blocks of U.T @ V  (reference :139-178)."""
+    o, g = u_dblocks.shape[0], u_offdblocks.shape[0]
+    ff = torch.matmul(u_dblocks.transpose(1, 2), v_dblocks)
+    gg = torch.matmul(u_offdblocks.transpose(1, 2), v_offdblocks)
+    if g == o:
+        return torch.cat([ff[:1], ff[1:] + gg[: o - 1], gg[o - 1:]], dim=0)
+    return torch.cat([ff[:1], ff[1:] + gg], dim=0)
+
+
+def interleave(a, b):
+    """V[::2] = a, V[1::2] = b; what is left of the longer one is appended  (reference :181-200)."""
+    k = min(a.shape[0], b.shape[0])
+    head = torch.stack([a[:k], b[:k]], dim=1).reshape((2 * k,) + tuple(a.shape[1:]))
+    return torch.cat([head, a[k:], b[k:]], dim=0)
+
+
+# ---------------------------------------------------------------------------------------
+# factorisation
+# ---------------------------------------------------------------------------------------
+def _to_caller(t, batched, caller):
+    t = t if batched else t[0]
+    return t if t.device == caller else t.to(caller)
+
+
+def decompose_step(Rs, Os):
+    """One CR level  (reference :204-259):
+    returns ``(num_dblocks, Ks_even, F, G), (Rs_next, Os_next)``."""
+    _check_blocks(Rs, Os)
+    dev = _engine.require_cuda()
+    batched, caller = Rs.dim() == 4, Rs.device
+    R = _batched(_dev(Rs, dev), batched)
+    O = _batched(_dev(Os, dev), batched)
+    pack = _engine.forward_sweep(R, O, None, keep_factors=True, want_logdet=False, nlevels=1)
+    pack.check()
+    B, ell = R.shape[0], R.shape[2]
+    m = R.shape[1]
+    E, o, g = _engine.counts(m)
+    z = lambda rows: torch.empty((B, rows, ell, ell), dtype=R.dtype, device=dev)
+    K = pack.D[0]
+    F = pack.F[0] if o > 0 else z(0)
+    G = pack.G[0] if g > 0 else z(0)
+    Rn, On, _ = pack.rest if pack.rest is not None else (None, None, None)
+    Rn = Rn if Rn is not None else z(0)
+    On = On if On is not None else z(0)
+    c = lambda t: _to_caller(t, batched, caller)
+    return (m, c(K), c(F), c(G)), (c(Rn), c(On))
+
+
+def _decompose_impl(Rs, Os):
+    _check_blocks(Rs, Os)
+    dev = _engine.require_cuda()
+    batched, caller = Rs.dim() == 4, Rs.device
+    R = _batched(_dev(Rs, dev), batched)
+    O = _batched(_dev(Os, dev), batched)
+    pack = _engine.forward_sweep(R, O, None, keep_factors=True)
+    pack.check()
+    ell = R.shape[2]
+    z = torch.empty((R.shape[0], 0, ell, ell), dtype=R.dtype, device=dev)
+    c = lambda t: _to_caller(t, batched, caller)
+    Ds = [c(d) for d in pack.D]
+    Fs = [c(f) for k, f in enumerate(pack.F[:-1])]
+    Gs = [c(g) if _engine.counts(pack.ms[k])[2] > 0 else c(z) for k, g in enumerate(pack.G[:-1])]
+    ms = torch.tensor(pack.ms, dtype=torch.int64)
+    return CRDecomp(ms, Ds, Fs, Gs, pack=pack, Rs=Rs, Os=Os, batched=batched, caller_device=caller)
+
+
+def decompose(Rs, Os):
+    """Full CR factorisation  (reference :288-309): ``(ms, Ds, Fs, Gs)`` with ``ms`` an
+    int64 tensor ``[n, n//2, ..., 1]`` and per-level lists of ``(E_k,l,l)``, ``(o_k,l,l)``,
+    ``(g_k,l,l)`` tensors (lower-triangular Cholesky factors in ``Ds``)."""
+    return _decompose_impl(Rs, Os)
+
+
+# ---------------------------------------------------------------------------------------
+# solves
+# ---------------------------------------------------------------------------------------
+def halfsolve(decomp, y):
+    """L^{-1} T y in CR order: list of per-level ``(E_k, l)`` tensors  (reference :312-338)."""
+    pack, batched, caller = _pack_of(decomp)
+    dev = _engine.require_cuda()
+    Y = _batched(_dev(y, dev, pack.dtype), batched)
+    X, _ = _engine.halfsolve_sweep(pack, Y)
+    return [_to_caller(x, batched, y.device) for x in X]
+
+
+def backhalfsolve(decomp, ycrr):
+    """T^T L^{-T} y for ``ycrr`` in CR order  (reference :341-377); returns ``(n, l)``."""
+    pack, batched, caller = _pack_of(decomp)
+    dev = _engine.require_cuda()
+    xs = _vec_levels(pack, ycrr, batched, dev)
+    _, _, w = _engine.backward_sweep(pack, sigma=False, w=True, xs=xs)
+    return _to_caller(w, batched, ycrr[0].device)
+
+
+def solve(decomp, y):
+    """J^{-1} y  (reference :441-444)."""
+    pack, batched, caller = _pack_of(decomp)
+    dev = _engine.require_cuda()
+    Y = _batched(_dev(y, dev, pack.dtype), batched)
+    X, _ = _engine.halfsolve_sweep(pack, Y)
+    _, _, w = _engine.backward_sweep(pack, sigma=False, w=True, xs=X)
+    return _to_caller(w, batched, y.device)
+
+
+def mahal(decomp, y):
+    """y^T J^{-1} y  (reference :461-467)."""
+    pack, batched, caller = _pack_of(decomp)
+    dev = _engine.require_cuda()
+    Y = _batched(_dev(y, dev, pack.dtype), batched)
+    _, acc = _engine.halfsolve_sweep(pack, Y, want_mahal=True)
+    out = acc.to(pack.dtype)
+    out = out if batched else out[0]
+    return out.to(y.device)
+
+
+def inverse_blocks(decomp):
+    """Diagonal and lower off-diagonal blocks of J^{-1}  (reference :470-503):
+    ``(Sig_diag:(n,l,l), Sig_off:(n-1,l,l))`` with ``Sig_off[i] = (J^{-1})_{i+1,i}``."""
+    pack, batched, caller = _pack_of(decomp)
+    Sd, So, _ = _engine.backward_sweep(pack, sigma=True, w=False)
+    return _to_caller(Sd, batched, caller), _to_caller(So, batched, caller)
+
+
+# ---------------------------------------------------------------------------------------
+# log-determinant and the fused likelihood pass, with hand-written backward
+# ---------------------------------------------------------------------------------------
+class _LogDetFn(torch.autograd.Function):
+    """log|J| of an existing factorisation; d/dR_i = Sigma_ii, d/dO_i = 2 Sigma_{i+1,i}."""
+
+    @staticmethod
+    def forward(ctx, Rs, Os, decomp):
+        pack = decomp._pack
+        ctx.pack, ctx.batched, ctx.caller = pack, decomp._batched, Rs.device
+        out = pack.logdet.to(pack.dtype)
+        out = out if decomp._batched else out[0]
+        return out.to(Rs.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        pack = ctx.pack
+        dev = pack.D[0].device
+        gd = g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
+        gm = torch.zeros_like(gd)
+        gR, gO, _ = _engine.backward_sweep(pack, sigma=True, w=False, grad=(gm, gd))
+        return _to_caller(gR, ctx.batched, ctx.caller), _to_caller(gO, ctx.batched, ctx.caller), None
+
+
+def det(decomp):
+    """log|J| = 2 sum log diag(D)  (reference :447-458; it is a log-determinant despite
+    the name).  Differentiable wrt the ``Rs``/``Os`` that were handed to ``decompose``."""
+    if isinstance(decomp, CRDecomp) and decomp._pack is not None:
+        return _LogDetFn.apply(decomp._Rs, decomp._Os, decomp)
+    ms, Ds, Fs, Gs = decomp
+    total = sum(torch.log(torch.diagonal(D, dim1=-2, dim2=-1)).sum(dim=(-1, -2)) for D in Ds)
+    return 2 * total
+
+
+class _MahalAndDetFn(torch.autograd.Function):
+    """(x^T J^{-1} x, log|J|) in one forward sweep; backward = back-solve + selected inverse
+    with the gradient assembled inside the level-0 kernel."""
+
+    @staticmethod
+    def forward(ctx, Rs, Os, x, batched):
+        dev = _engine.require_cuda()
+        R = _batched(_dev(Rs, dev), batched)
+        O = _batched(_dev(Os, dev), batched)
+        X = _batched(_dev(x, dev, Rs.dtype), batched)
+        need = any(ctx.needs_input_grad[:3])
+        pack = _engine.forward_sweep(R, O, X, keep_factors=need)
+        pack.check()
+        ctx.pack = pack if need else None
+        ctx.batched, ctx.devs = batched, (Rs.device, Os.device, x.device)
+        mh, ld = pack.mahal.to(Rs.dtype), pack.logdet.to(Rs.dtype)
+        if not batched:
+            mh, ld = mh[0], ld[0]
+        return mh.to(Rs.device), ld.to(Rs.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_mahal, g_det):
+        pack = ctx.pack
+        dev = pack.D[0].device
+        as_vec = lambda g: g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
+        gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(as_vec(g_mahal), as_vec(g_det)))
+        b = ctx.batched
+        return (_to_caller(gR, b, ctx.devs[0]), _to_caller(gO, b, ctx.devs[1]), _to_caller(gx, b, ctx.devs[2]), None)
+
+
+def mahal_and_det(Rs, Os, x):
+    """``(x^T J^{-1} x, log|J|)`` without keeping the factorisation  (reference :380-438).
+    Under autograd the factors are kept for the hand-written backward instead of a tape."""
+    _check_blocks(Rs, Os)
+    batched = Rs.dim() == 4
+    if x.dim() != Rs.dim() - 1 or x.shape[-2] != Rs.shape[-3] or x.shape[-1] != Rs.shape[-1]:
+        raise TypeError("x must be (n,l) (or (B,n,l)) matching Rs")
+    return _MahalAndDetFn.apply(Rs, Os, x, batched)

@@ -1,0 +1,50 @@
+"""Synthetic LEG posterior-precision blocks on the GPU, for benchmarks and full-size tests
+(SURVEY 8(d)).  Restates ``LEGFamily.compute_PEG_precision`` / ``compute_posterior_precision``
+of the reference (cyclic_gps/models.py:181-239, 254-268) in batched torch ops; always built in
+fp64 from fp64 time gaps and cast at the end (fp32 time stamps cannot resolve unit gaps at
+n >= 1e7).  Input generation only -- not part of the timed hot path."""
+import torch
+
+
+def leg_params(rank: int, seed: int = 0, device="cpu"):
+    """(G, B, LL^T) exactly as a fresh ``LEGFamily(rank, obs_dim=1)`` builds them
+    (models.py:93-121, 152-166): N = I, R = strictly-lower part of 0.2 (A - A^T), B = 0.5/sqrt(rank),
+    Lambda = softplus(0.1)."""
+    gen = torch.Generator().manual_seed(seed)
+    eye = torch.eye(rank, dtype=torch.float64)
+    A = torch.randn((rank, rank), generator=gen, dtype=torch.float64)
+    Rm = torch.tril((A - A.T) * 0.2, diagonal=-1)
+    B = torch.full((1, rank), 0.5 / rank ** 0.5, dtype=torch.float64)
+    lam = torch.nn.functional.softplus(torch.tensor([[0.1]], dtype=torch.float64))
+    G = eye + Rm - Rm.T + 1e-5 * eye
+    LLT = lam @ lam.T + 1e-9 * torch.eye(1, dtype=torch.float64)
+    return G.to(device), B.to(device), LLT.to(device)
+
+
+def leg_precision_blocks(gaps, G, B, LLT, dtype, chunk: int = 1 << 20):
+    """gaps (..., n-1) fp64 -> Rs (..., n, l, l), Os (..., n-1, l, l) of
+    K = Sigma^{-1} + B^T (LL^T)^{-1} B, in `dtype`.  Processed in chunks of gaps to bound memory."""
+    lead, nm1 = gaps.shape[:-1], gaps.shape[-1]
+    l = G.shape[0]
+    flat = gaps.reshape(-1, nm1)
+    S = flat.shape[0]
+    dev = gaps.device
+    eye = torch.eye(l, dtype=torch.float64, device=dev)
+    shift = eye + B.T @ torch.linalg.solve(LLT, B)
+    Rs = torch.empty((S, nm1 + 1, l, l), dtype=dtype, device=dev)
+    Os = torch.empty((S, nm1, l, l), dtype=dtype, device=dev)
+    evals, evecs = torch.linalg.eig(G.cpu())                   # G is tiny; eigendecompose once (model_utils.py:12-29)
+    evals, evecs = evals.to(dev), evecs.to(dev)
+    evecs_inv = torch.linalg.inv(evecs)
+    for s in range(S):
+        Rs[s] = shift.to(dtype)
+        for a in range(0, nm1, chunk):
+            d = flat[s, a:a + chunk]
+            A = ((evecs.unsqueeze(0) * torch.exp(-0.5 * d.reshape(-1, 1, 1) * evals.reshape(1, 1, -1))) @ evecs_inv).real
+            At = A.transpose(1, 2)
+            right = torch.linalg.solve(eye - A @ At, A)          # (I - A A^T)^{-1} A
+            left = torch.linalg.solve(eye - At @ A, At)          # (I - A^T A)^{-1} A^T
+            Os[s, a:a + chunk] = (-right).to(dtype)
+            Rs[s, a + 1:a + chunk + 1] += (A @ left).to(dtype)   # contribution of gap i to row i+1
+            Rs[s, a:a + d.shape[0]] += (At @ right).to(dtype)    # contribution of gap i to row i
+    return Rs.reshape(*lead, nm1 + 1, l, l), Os.reshape(*lead, nm1, l, l)

@@ -1,0 +1,98 @@
+/* crb200 -- C ABI of the B200-native block cyclic-reduction (CR) engine.
+ *
+ * Drop-in boundary for the hot path of cunningham-lab/cyclic-gps: the module-level
+ * functions of cyclic_gps/cyclic_reduction.py (the reference has no FFI; its "interface" is
+ * that Python module, imported at cyclic_gps/models.py:10).  Each entry below names the
+ * reference code it replaces.  The library allocates nothing, keeps no global state, takes
+ * raw DEVICE pointers plus a cudaStream_t (as void*), is re-entrant and may be called from any
+ * host thread (the autograd engine calls the backward entries from its own thread).
+ *
+ * Conventions
+ *   dtype     CRB200_F32 / CRB200_F64; all arrays of one call share it.
+ *   ell       block size, 1 <= ell <= crb200_max_ell().
+ *   level     a symmetric positive-definite block-tridiagonal system with m block rows:
+ *             R (batch, m, ell, ell) diagonal blocks (only the lower triangle is read by the
+ *             factorisation), O (batch, m-1, ell, ell) lower off-diagonal blocks
+ *             (O[i] = J_{i+1,i}), y (batch, m, ell).  Row-major, contiguous per series.
+ *   counts    E = ceil(m/2) even (eliminated) nodes, o = floor(m/2) odd (surviving) nodes,
+ *             g = floor((m-1)/2) G links.
+ *   return    0 ok; <0 = CRB200_E*.  Non-positive-definite blocks do not fail the call:
+ *             they are reported through `info` (see crb200_fwd_args) and produce NaNs.
+ */
+#ifndef CRB200_H_
+#define CRB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB200_F32 0
+#define CRB200_F64 1
+
+#define CRB200_OK 0
+#define CRB200_EINVAL (-1)        /* null / inconsistent argument                      */
+#define CRB200_EUNSUPPORTED (-2)  /* ell or dtype outside the compiled range           */
+#define CRB200_ECUDA (-3)         /* CUDA launch error; see crb200_last_cuda_error()   */
+
+/* One CR level, forward.  Replaces decompose_step (cyclic_reduction.py:204-259) fused with
+ * the per-level bodies of mahal_and_det (:412-427) and halfsolve (:318-333). */
+typedef struct crb200_fwd_args {
+  int batch, m;
+  const void* R; const void* O; const void* y;        /* y may be NULL (factor only)              */
+  long long strideR, strideO, stridey;                /* series strides of R, O, y in ELEMENTS     */
+  void* D; void* F; void* G; void* xk;                /* out: K (batch,E,l,l) lower-tri, F (batch,o,l,l),
+                                                         G (batch,g,l,l), x_k (batch,E,l).  D/F/G all NULL
+                                                         => factors not kept; xk NULL => not stored  */
+  void* Rn; void* On; void* yn;                       /* out: reduced system (batch,o,..),(batch,o-1,..),(batch,o,l) */
+  double* logdet; double* mahal;                      /* in/out per-series accumulators (+= sum log diag K,
+                                                         += |x_k|^2), NULL to skip                   */
+  int* info;                                          /* in/out: max over failures of INT_MAX - (series*E + e);
+                                                         caller zero-initialises; 0 = all blocks PD  */
+  /* left halo (chunk-partitioned series): virtual surviving node -1 coupled to row 0 by O_halo */
+  const void* O_halo; void* G_halo; void* On_halo; void* Rh_acc; void* yh_acc;   /* (batch,l,l)x4, (batch,l) */
+} crb200_fwd_args;
+
+/* One CR level, backward direction (deepest level first).  Replaces the per-level bodies of
+ * backhalfsolve (:362-373) and inverse_blocks (:478-501); with grad_mode it also assembles
+ * the gradient of gm*mahal + gd*logdet wrt (R, O, x) that torch autograd produces through
+ * the reference (models.py:374-381). */
+typedef struct crb200_bwd_args {
+  int batch, m;
+  const void* D; const void* F; const void* G; const void* xk;   /* factors of this level            */
+  const void* Sd_in; const void* So_in; const void* w_in;        /* deeper level: (batch,o,..),(batch,o-1,..),(batch,o,l) */
+  void* Sd_out; void* So_out; void* w_out;                       /* out: (batch,m,..),(batch,m-1,..),(batch,m,l);
+                                                                    Sd_out/So_out NULL => solve only;
+                                                                    w_out NULL => selected inverse only */
+  long long strideSd, strideSo, stridew;                         /* series strides of the outputs (elements) */
+  const double* gm; const double* gd;                            /* per-series cotangents (grad_mode)  */
+  int grad_mode;                                                 /* 0: Sigma / w ; 1: gR / gO / gx     */
+  const void* G_halo; const void* Sd_halo; const void* w_halo; const void* So_halo_in; void* So_halo_out;
+} crb200_bwd_args;
+
+/* Half solve against stored factors.  Replaces one iteration of halfsolve (:318-333):
+ * x_k = D^{-1} y[0::2];  yn = y[1::2] - U x_k (Ux :40-60);  mahal += |x_k|^2 (mahal :461-467). */
+typedef struct crb200_hs_args {
+  int batch, m;
+  const void* D; const void* F; const void* G;
+  const void* y; long long stridey;
+  void* xk; void* yn;
+  double* mahal;
+} crb200_hs_args;
+
+int crb200_version(void);
+int crb200_max_ell(void);
+/* cudaError_t of the last failing launch on the calling thread's most recent call (0 if none). */
+int crb200_last_cuda_error(void);
+
+int crb200_level_fwd(int dtype, int ell, const crb200_fwd_args* args, void* stream);
+int crb200_level_bwd(int dtype, int ell, const crb200_bwd_args* args, void* stream);
+int crb200_level_halfsolve(int dtype, int ell, const crb200_hs_args* args, void* stream);
+
+/* Tile geometry, for the roofline bookkeeping in bench.py: even nodes owned per CTA. */
+int crb200_fwd_tile_nodes(int dtype, int ell);
+int crb200_bwd_tile_nodes(int dtype, int ell);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB200_H_ */

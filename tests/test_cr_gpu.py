@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python API)
+against the CPU oracle and the golden vectors of the unmodified reference.
+
+Tolerances are BASELINE.json's: relative 1e-10 in fp64 and 1e-4 in fp32, where relative means
+max-abs-error / max-abs-reference per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL, assert_close, relerr, split_levels
+from oracle import cr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def cr():
+    from cyclic_gps import cyclic_reduction
+    return cyclic_reduction
+
+
+def leg_inputs(l, n, dtype, seed=0, spacing="irregular"):
+    g = torch.Generator().manual_seed(seed)
+    G, B, LLT = orc.leg_params(l, seed=seed)
+    if n == 1:
+        R = (torch.eye(l, dtype=torch.float64) + B.T @ torch.linalg.solve(LLT, B)).unsqueeze(0)
+        O = torch.zeros((0, l, l), dtype=torch.float64)
+    else:
+        gaps = (-torch.log(torch.rand(n - 1, generator=g, dtype=torch.float64)) + 0.01) if spacing == "irregular" \
+            else torch.ones(n - 1, dtype=torch.float64)
+        R, O = orc.leg_posterior_precision(gaps, G, B, LLT)
+    x = torch.randn((n, l), generator=g, dtype=torch.float64)
+    return R.to(dtype), O.to(dtype), x.to(dtype)
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+# ------------------------------------------------------------------ one level
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 8, 11, 16])
+def test_decompose_step_vs_oracle(l, dtype):
+    c = cr()
+    tol = TOL[dtype]
+    for m in [2, 3, 4, 5, 6, 7, 8, 9, 31, 32, 33, 63, 64, 65, 66, 127, 130, 257]:
+        if l >= 11 and m > 70:
+            continue
+        R, O, _ = leg_inputs(l, m, dtype, seed=m)
+        (mm, K, F, G), (Rn, On) = c.decompose_step(R, O)
+        (m2, K2, F2, G2), (Rn2, On2) = orc.level_step(R.double(), O.double())
+        assert mm == m2 and K.device == R.device
+        for a, b, name in ((K, K2, "K"), (F, F2, "F"), (G, G2, "G"), (Rn, Rn2, "Rn"), (On, On2, "On")):
+            assert tuple(a.shape) == tuple(b.shape), (name, m, a.shape, b.shape)
+            assert_close(a, b, tol, f"{name} l={l} m={m}")
+        assert torch.equal(torch.triu(K, diagonal=1), torch.zeros_like(K))   # exact zeros above the diagonal
+
+
+# ------------------------------------------------------------------ golden vectors
+def _check_golden_case(g, p, tol):
+    c = cr()
+    R, O, x = _t(g[p + "R"]), _t(g[p + "O"]), _t(g[p + "x"])
+    l = R.shape[1]
+    dec = c.decompose(R, O)
+    ms, Ds, Fs, Gs = dec
+    assert ms.dtype == torch.int64 and np.array_equal(ms.numpy(), g[p + "ms"])
+    assert len(Ds) == len(ms) and len(Fs) == len(ms) - 1 and len(Gs) == len(ms) - 1
+    if (p + "D") in g.files:
+        for name, lv in (("D", Ds), ("F", Fs), ("G", Gs)):
+            want = split_levels(g[p + name], g[p + name + "_counts"], (l, l))
+            for k, (a, b) in enumerate(zip(lv, want)):
+                assert tuple(a.shape) == tuple(b.shape), (name, k)
+                assert_close(a, b, tol, f"{p}{name}[{k}]")
+    hs = c.halfsolve(dec, x)
+    want = split_levels(g[p + "halfsolve"], g[p + "halfsolve_counts"], (l,))
+    assert len(hs) == len(want)
+    for a, b in zip(hs, want):
+        assert_close(a, b, tol, p + "halfsolve")
+    assert_close(c.solve(dec, x), g[p + "solve"], tol, p + "solve")
+    assert_close(c.det(dec), g[p + "logdet"], tol, p + "det")
+    assert_close(c.mahal(dec, x), g[p + "mahal"], tol, p + "mahal")
+    mm, dd = c.mahal_and_det(R, O, x)
+    assert mm.dim() == 0 and dd.dim() == 0 and mm.dtype == R.dtype
+    assert_close(mm, g[p + "mahal_fused"], tol, p + "mahal_and_det[0]")
+    assert_close(dd, g[p + "logdet_fused"], tol, p + "mahal_and_det[1]")
+    Sd, So = c.inverse_blocks(dec)
+    assert_close(Sd, g[p + "Sd"], tol, p + "inverse diag")
+    assert_close(So, g[p + "So"], tol, p + "inverse off")
+    counts = [(int(m) + 1) // 2 for m in g[p + "ms"]]
+    ycrr = split_levels(g[p + "ycrr"], counts, (l,))
+    assert_close(c.backhalfsolve(dec, ycrr), g[p + "backhalfsolve"], tol, p + "backhalfsolve")
+    for tag, (gm, gd) in (("11", (1.0, 1.0)), ("ab", (0.3, -0.7))):
+        Rr, Or, xr = [t.clone().requires_grad_(True) for t in (R, O, x)]
+        m2, d2 = c.mahal_and_det(Rs=Rr, Os=Or, x=xr)
+        (gm * m2 + gd * d2).backward()
+        assert_close(Rr.grad, g[p + "gR_" + tag], tol, p + "gR " + tag)
+        if O.numel():
+            assert_close(Or.grad, g[p + "gO_" + tag], tol, p + "gO " + tag)
+        assert_close(xr.grad, g[p + "gx_" + tag], tol, p + "gx " + tag)
+
+
+def test_golden_leg(golden):
+    g = golden["leg"]
+    for p in g["cases"]:
+        p = str(p)
+        _check_golden_case(g, p, 1e-4 if "float32" in p else 1e-10)
+
+
+def test_golden_random_llt(golden):
+    # the reference test's own generator (J = L L^T, ill-conditioned): same checks the reference
+    # makes, with np.allclose defaults against dense numpy, plus tight comparison with the reference's CR
+    g = golden["random_llt"]
+    c = cr()
+    for p in g["cases"]:
+        p = str(p)
+        _check_golden_case(g, p, 1e-8)
+        R, O, x = _t(g[p + "R"]), _t(g[p + "O"]), _t(g[p + "x"])
+        dec = c.decompose(R, O)
+        assert np.allclose(c.det(dec).numpy(), g[p + "dense_logdet"])
+        assert np.allclose(c.solve(dec, x).numpy(), g[p + "dense_solve"])
+
+
+def test_golden_known_matrices(golden):
+    # reference tests/test_cyclic_reduction.py:243-291 (fp32, closed forms, np.allclose defaults)
+    g = golden["known"]
+    c = cr()
+    x = _t(g["x"])
+    for name, l in (("bab", 1), ("schur", 2)):
+        R, O = _t(g[name + "_R"]), _t(g[name + "_O"])
+        assert R.dtype == torch.float32
+        dec = c.decompose(R, O)
+        mm, dd = c.mahal_and_det(R, O, x=x.reshape(-1, l))
+        assert np.allclose(g[name + "_logdet_closed"], c.det(dec).numpy())
+        assert np.allclose(g[name + "_logdet_closed"], dd.numpy())
+        Sd, So = c.inverse_blocks(dec)
+        assert np.allclose(g[name + "_inv_R_closed"], Sd.numpy())
+        assert np.allclose(g[name + "_inv_O_closed"], So.numpy())
+        assert np.allclose(g[name + "_mahal_closed"], mm.numpy())
+
+
+# ------------------------------------------------------------------ bigger cases vs the oracle
+@pytest.mark.parametrize("l,n,dtype", [(3, 1000, torch.float64), (8, 4097, torch.float32), (4, 10000, torch.float32),
+                                         (16, 502, torch.float64), (2, 3000, torch.float64), (32, 70, torch.float64),
+                                         (24, 40, torch.float32), (8, 1023, torch.float64)])
+def test_full_path_vs_oracle(l, n, dtype):
+    c = cr()
+    tol = TOL[dtype]
+    R, O, x = leg_inputs(l, n, dtype, seed=l * 7 + n)
+    Rd, Od, xd = R.double(), O.double(), x.double()
+    dec_o = orc.factor(Rd, Od)
+    dec = c.decompose(R.cuda(), O.cuda())
+    assert dec[1][0].is_cuda
+    assert_close(c.det(dec), orc.logdet(dec_o), tol, "logdet")
+    assert_close(c.solve(dec, x.cuda()), orc.solve(dec_o, xd), tol, "solve")
+    assert_close(c.mahal(dec, x.cuda()), orc.mahal(dec_o, xd), tol, "mahal")
+    Sd, So = c.inverse_blocks(dec)
+    Sd_o, So_o = orc.selected_inverse(dec_o)
+    assert_close(Sd, Sd_o, tol, "Sigma diag")
+    assert_close(So, So_o, tol, "Sigma off")
+    Rr, Or, xr = [t.cuda().requires_grad_(True) for t in (R, O, x)]
+    mm, dd = c.mahal_and_det(Rr, Or, xr)
+    (0.5 * mm - 1.5 * dd).backward()
+    gR, gO, gx = orc.loglik_grads(Rd, Od, xd, 0.5, -1.5)
+    assert_close(mm, orc.mahal(dec_o, xd), tol, "mahal fused")
+    assert_close(Rr.grad, gR, tol, "gR")
+    assert_close(Or.grad, gO, tol, "gO")
+    assert_close(xr.grad, gx, tol, "gx")
+
+
+def test_det_of_decompose_is_differentiable():
+    c = cr()
+    R, O, _ = leg_inputs(4, 300, torch.float64, seed=5)
+    Rr, Or = R.clone().requires_grad_(True), O.clone().requires_grad_(True)
+    ld = c.det(c.decompose(Rr, Or))
+    (2.0 * ld).backward()
+    gR, gO, _ = orc.loglik_grads(R, O, torch.zeros(300, 4, dtype=torch.float64), 0.0, 2.0)
+    assert_close(Rr.grad, gR, 1e-10, "d logdet / dR")
+    assert_close(Or.grad, gO, 1e-10, "d logdet / dO")
+
+
+def test_batched_equals_loop():
+    c = cr()
+    B, n, l = 5, 77, 3
+    cases = [leg_inputs(l, n, torch.float64, seed=40 + b) for b in range(B)]
+    R = torch.stack([k[0] for k in cases]).cuda()
+    O = torch.stack([k[1] for k in cases]).cuda()
+    x = torch.stack([k[2] for k in cases]).cuda()
+    Rr, Or, xr = R.clone().requires_grad_(True), O.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    mm, dd = c.mahal_and_det(Rr, Or, xr)
+    assert mm.shape == (B,) and dd.shape == (B,)
+    wts = torch.linspace(0.5, 1.5, B, dtype=torch.float64, device="cuda")
+    ((wts * mm).sum() + (dd / wts).sum()).backward()
+    dec = c.decompose(R, O)
+    w = c.solve(dec, x)
+    Sd, So = c.inverse_blocks(dec)
+    for b in range(B):
+        Rb, Ob, xb = cases[b]
+        dec_o = orc.factor(Rb, Ob)
+        assert_close(mm[b], orc.mahal(dec_o, xb), 1e-10)
+        assert_close(dd[b], orc.logdet(dec_o), 1e-10)
+        assert_close(w[b], orc.solve(dec_o, xb), 1e-10)
+        sd, so = orc.selected_inverse(dec_o)
+        assert_close(Sd[b], sd, 1e-10)
+        assert_close(So[b], so, 1e-10)
+        gR, gO, gx = orc.loglik_grads(Rb, Ob, xb, float(wts[b]), float(1 / wts[b]))
+        assert_close(Rr.grad[b], gR, 1e-10)
+        assert_close(Or.grad[b], gO, 1e-10)
+        assert_close(xr.grad[b], gx, 1e-10)
+
+
+def test_edge_cases():
+    c = cr()
+    # n = 1: ms = [1], no F / G   (must work)
+    R, O, x = leg_inputs(3, 1, torch.float64)
+    dec = c.decompose(R, O)
+    ms, Ds, Fs, Gs = dec
+    assert ms.tolist() == [1] and len(Ds) == 1 and Fs == [] and Gs == []
+    assert_close(c.det(dec), torch.logdet(R[0]), 1e-12)
+    assert_close(c.solve(dec, x), torch.linalg.solve(R[0], x[0]).unsqueeze(0), 1e-12)
+    assert_close(c.inverse_blocks(dec)[0], torch.linalg.inv(R[0]).unsqueeze(0), 1e-12)
+    assert c.inverse_blocks(dec)[1].shape == (0, 3, 3)
+    # n = 2, l = 1
+    R = torch.tensor([[[4.0]], [[9.0]]], dtype=torch.float64)
+    O = torch.tensor([[[1.0]]], dtype=torch.float64)
+    mm, dd = c.mahal_and_det(R, O, torch.tensor([[1.0], [2.0]], dtype=torch.float64))
+    J = torch.tensor([[4.0, 1.0], [1.0, 9.0]], dtype=torch.float64)
+    v = torch.tensor([1.0, 2.0], dtype=torch.float64)
+    assert_close(dd, torch.logdet(J), 1e-12)
+    assert_close(mm, v @ torch.linalg.solve(J, v), 1e-12)
+    # shape errors mirror the reference's assertion (cyclic_reduction.py:223)
+    with pytest.raises(AssertionError):
+        c.decompose(torch.eye(2).repeat(3, 1, 1), torch.eye(2).repeat(3, 1, 1))
+    # non positive definite input raises instead of returning NaNs
+    Rbad = torch.eye(2, dtype=torch.float64).repeat(4, 1, 1)
+    Rbad[2] = -Rbad[2]
+    with pytest.raises(c.NotPositiveDefiniteError):
+        c.decompose(Rbad, torch.zeros(3, 2, 2, dtype=torch.float64))
+    # keyword call used by the reference model (models.py:290,367)
+    R, O, x = leg_inputs(2, 9, torch.float64)
+    c.decompose(**{"Rs": R, "Os": O})
+    c.mahal_and_det(Rs=R, Os=O, x=x)
+
+
+def test_plain_tuple_decomp_is_accepted():
+    c = cr()
+    R, O, x = leg_inputs(3, 40, torch.float64, seed=3)
+    ms, Ds, Fs, Gs = orc.factor(R, O)     # a decomposition that did not come from our decompose()
+    plain = (ms, Ds, Fs, Gs)
+    dec_o = (ms, Ds, Fs, Gs)
+    assert_close(c.solve(plain, x), orc.solve(dec_o, x), 1e-10)
+    assert_close(c.det(plain), orc.logdet(dec_o), 1e-12)
+    Sd, So = c.inverse_blocks(plain)
+    sd, so = orc.selected_inverse(dec_o)
+    assert_close(Sd, sd, 1e-10)
+    assert_close(So, so, 1e-10)
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def _tridiag_matvec(R, O, w):
+    out = torch.einsum("bnij,bnj->bni", R, w)
+    out[:, 1:] += torch.einsum("bnij,bnj->bni", O, w[:, :-1])
+    out[:, :-1] += torch.einsum("bnji,bnj->bni", O, w[:, 1:])
+    return out
+
+
+def test_config2_shape_properties():
+    """B x n = 256 x 10^4, l = 8, fp32 (a quarter of BASELINE config 2's batch): residual of the
+    solve, linearity of the solve, and gradient identity gx = 2 gm J^{-1} x."""
+    c = cr()
+    B, n, l = 256, 10000, 8
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    G, Bm, LLT = orc.leg_params(l, seed=0)
+    gaps = (-torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64, device="cuda")) + 0.01)
+    from cyclic_gps.synth import leg_precision_blocks
+    R, O = leg_precision_blocks(gaps, G.cuda(), Bm.cuda(), LLT.cuda(), torch.float32)
+    x = torch.randn((B, n, l), generator=gen, dtype=torch.float32, device="cuda")
+    dec = c.decompose(R, O)
+    w = c.solve(dec, x)
+    res = _tridiag_matvec(R.double(), O.double(), w.double()) - x.double()
+    assert float(res.abs().max() / x.abs().max()) < 1e-4
+    w2 = c.solve(dec, 2.0 * x)
+    assert relerr(w2, 2.0 * w) < 1e-6
+    xr = x.clone().requires_grad_(True)
+    mm, dd = c.mahal_and_det(R, O, xr)
+    mm.sum().backward()
+    assert relerr(xr.grad, 2.0 * w) < 1e-4
+    assert relerr(mm, (x.double() * w.double()).sum(dim=(1, 2))) < 1e-4
+    # three series against the oracle
+    for b in (0, 100, 255):
+        dec_o = orc.factor(R[b].double().cpu(), O[b].double().cpu())
+        assert_close(dd[b], orc.logdet(dec_o), 1e-4)
+        assert_close(w[b], orc.solve(dec_o, x[b].double().cpu()), 1e-4)
