@@ -17,6 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcrb200.so")
 BUILD = os.path.join(HERE, "build")
+STAMP = os.path.join(HERE, "libcrb200.stamp")
 RANGES = [(1, 4), (5, 8), (9, 12), (13, 16), (17, 20), (21, 24), (25, 28), (29, 32)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
@@ -50,7 +51,7 @@ def _run(cmd):
 
 
 def is_current():
-    stamp = os.path.join(BUILD, "stamp")
+    stamp = STAMP
     return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash()
 
 
@@ -75,7 +76,7 @@ def build(force=False, jobs=None, verbose=False):
             if verbose and out.strip():
                 print(out)
     _run([nvcc, "-shared", "-o", OUT] + [u[0] for u in units] + ["-lcudart"])
-    with open(os.path.join(BUILD, "stamp"), "w") as fh:
+    with open(STAMP, "w") as fh:
         fh.write(source_hash())
     return OUT
 

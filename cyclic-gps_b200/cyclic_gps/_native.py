@@ -128,19 +128,30 @@ def _fill(struct, fields):
     return struct
 
 
+# Optional launch tracer (bench.py): an object with begin(kind, dtype, ell, batch, m) -> token
+# and end(token); called around every native launch on the current stream.
+TRACE = None
+
+
+def _traced(kind, fn, dtype, ell, a):
+    tr = TRACE
+    tok = tr.begin(kind, dtype, ell, a.batch, a.m) if tr is not None else None
+    rc = fn(dtype_code(dtype), ell, C.byref(a), _stream())
+    if tr is not None:
+        tr.end(tok)
+    _check(rc, "crb200_level_" + kind)
+
+
 def level_fwd(dtype: torch.dtype, ell: int, **fields):
-    a = _fill(FwdArgs(), fields)
-    _check(load().crb200_level_fwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_fwd")
+    _traced("fwd", load().crb200_level_fwd, dtype, ell, _fill(FwdArgs(), fields))
 
 
 def level_bwd(dtype: torch.dtype, ell: int, **fields):
-    a = _fill(BwdArgs(), fields)
-    _check(load().crb200_level_bwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_bwd")
+    _traced("bwd", load().crb200_level_bwd, dtype, ell, _fill(BwdArgs(), fields))
 
 
 def level_halfsolve(dtype: torch.dtype, ell: int, **fields):
-    a = _fill(HsArgs(), fields)
-    _check(load().crb200_level_halfsolve(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_level_halfsolve")
+    _traced("halfsolve", load().crb200_level_halfsolve, dtype, ell, _fill(HsArgs(), fields))
 
 
 def tile_nodes(dtype: torch.dtype, ell: int):
