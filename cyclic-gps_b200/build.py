@@ -55,8 +55,10 @@ def is_current():
     return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash()
 
 
-def build(force=False, jobs=None, verbose=False):
-    if not force and is_current():
+def build(force=False, jobs=None, verbose=False, only=None):
+    """only: e.g. "f32:5-8,f64:1-4" -> development build, every other (dtype, range) unit is a
+    stub that reports cudaErrorNotSupported (never leaves a `current` stamp behind)."""
+    if not force and only is None and is_current():
         return OUT
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
@@ -64,8 +66,9 @@ def build(force=False, jobs=None, verbose=False):
     for tn, ty in (("f32", "float"), ("f64", "double")):
         for lo, hi in RANGES:
             obj = os.path.join(BUILD, f"inst_{tn}_{lo}_{hi}.o")
-            units.append((obj, [nvcc] + NVCC_FLAGS + [f"-DCRB_T={ty}", f"-DCRB_TN={tn}", f"-DCRB_LO={lo}", f"-DCRB_HI={hi}",
-                                                       "-c", os.path.join(CSRC, "cr_inst.cu"), "-o", obj]))
+            stub = ["-DCRB_STUB"] if (only is not None and f"{tn}:{lo}-{hi}" not in only.split(",")) else []
+            units.append((obj, [nvcc] + NVCC_FLAGS + stub + [f"-DCRB_T={ty}", f"-DCRB_TN={tn}", f"-DCRB_LO={lo}", f"-DCRB_HI={hi}",
+                                                              "-c", os.path.join(CSRC, "cr_inst.cu"), "-o", obj]))
     abi_obj = os.path.join(BUILD, "cr_abi.o")
     units.append((abi_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_abi.cu"), "-o", abi_obj]))
     jobs = jobs or min(len(units), os.cpu_count() or 4)
@@ -77,7 +80,7 @@ def build(force=False, jobs=None, verbose=False):
                 print(out)
     _run([nvcc, "-shared", "-o", OUT] + [u[0] for u in units] + ["-lcudart"])
     with open(STAMP, "w") as fh:
-        fh.write(source_hash())
+        fh.write(source_hash() if only is None else "partial:" + only)
     return OUT
 
 
@@ -86,5 +89,6 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-j", type=int, default=None)
     ap.add_argument("-v", action="store_true")
+    ap.add_argument("--only", default=None, help='development build, e.g. "f32:5-8,f64:1-4"')
     a = ap.parse_args()
-    print(build(force=a.force, jobs=a.j, verbose=a.v))
+    print(build(force=a.force, jobs=a.j, verbose=a.v, only=a.only))

@@ -2,6 +2,8 @@
 // in parallel.  -DCRB_T=float|double -DCRB_TN=f32|f64 -DCRB_LO=.. -DCRB_HI=..
 #include "cr_level_fwd.cuh"
 #include "cr_level_bwd.cuh"
+#include "cr_tpn_fwd.cuh"
+#include "cr_tpn_bwd.cuh"
 #include "cr_halfsolve.cuh"
 
 #define CRB_CAT_(a, b, c, d) a##_##b##_##c##_##d
@@ -9,22 +11,51 @@
 
 namespace crb200 {
 
+#ifdef CRB_STUB
+// development builds (build.py --only ...): this (dtype, ell range) is compiled out
+cudaError_t CRB_CAT(inst_fwd, CRB_TN, CRB_LO, CRB_HI)(int, const LevelFwdArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t CRB_CAT(inst_bwd, CRB_TN, CRB_LO, CRB_HI)(int, const LevelBwdArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t CRB_CAT(inst_hs, CRB_TN, CRB_LO, CRB_HI)(int, const HalfSolveArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
+int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
+#else
+
 template <int L>
 struct Dispatch {
   static cudaError_t fwd(int ell, const LevelFwdArgs& a, cudaStream_t s) {
-    if (ell == L) return launch_level_fwd<CRB_T, L>(a, s);
+    if (ell == L) {
+      if constexpr (TpnFwdCfg<CRB_T, L>::ELIGIBLE) {
+        if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_fwd<CRB_T, L>(a, s);
+      } else {
+        if (a.variant == CRB200_THREAD_PER_NODE) return cudaErrorInvalidValue;
+      }
+      return launch_level_fwd<CRB_T, L>(a, s);
+    }
     return Dispatch<L + 1>::fwd(ell, a, s);
   }
   static cudaError_t bwd(int ell, const LevelBwdArgs& a, cudaStream_t s) {
-    if (ell == L) return launch_level_bwd<CRB_T, L>(a, s);
+    if (ell == L) {
+      if constexpr (TpnBwdCfg<CRB_T, L>::ELIGIBLE) {
+        if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_bwd<CRB_T, L>(a, s);
+      } else {
+        if (a.variant == CRB200_THREAD_PER_NODE) return cudaErrorInvalidValue;
+      }
+      return launch_level_bwd<CRB_T, L>(a, s);
+    }
     return Dispatch<L + 1>::bwd(ell, a, s);
   }
   static cudaError_t hs(int ell, const HalfSolveArgs& a, cudaStream_t s) {
     if (ell == L) return launch_level_halfsolve<CRB_T, L>(a, s);
     return Dispatch<L + 1>::hs(ell, a, s);
   }
-  static int fwd_tile(int ell) { return ell == L ? FwdCfg<CRB_T, L>::NG - 1 : Dispatch<L + 1>::fwd_tile(ell); }
-  static int bwd_tile(int ell) { return ell == L ? BwdCfg<CRB_T, L>::NG : Dispatch<L + 1>::bwd_tile(ell); }
+  static int fwd_tile(int ell) {
+    if (ell != L) return Dispatch<L + 1>::fwd_tile(ell);
+    return TpnFwdCfg<CRB_T, L>::ELIGIBLE ? TpnFwdCfg<CRB_T, L>::OWN : FwdCfg<CRB_T, L>::NG - 1;
+  }
+  static int bwd_tile(int ell) {
+    if (ell != L) return Dispatch<L + 1>::bwd_tile(ell);
+    return TpnBwdCfg<CRB_T, L>::ELIGIBLE ? TpnBwdCfg<CRB_T, L>::NT : BwdCfg<CRB_T, L>::NG;
+  }
 };
 template <>
 struct Dispatch<CRB_HI + 1> {
@@ -40,5 +71,6 @@ cudaError_t CRB_CAT(inst_bwd, CRB_TN, CRB_LO, CRB_HI)(int ell, const LevelBwdArg
 cudaError_t CRB_CAT(inst_hs, CRB_TN, CRB_LO, CRB_HI)(int ell, const HalfSolveArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::hs(ell, a, s); }
 int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::fwd_tile(ell); }
 int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::bwd_tile(ell); }
+#endif  // CRB_STUB
 
 }  // namespace crb200

@@ -1,0 +1,94 @@
+// Record-based staging for the thread-per-node kernels: one padded shared-memory record per
+// node, filled from / drained to flat coalesced global ranges by a single warp.
+//
+// All loops address shared memory through 32-bit shared-window addresses and walk global
+// memory with a running pointer, so a 16-byte chunk costs ~4 instructions (cp.async or
+// LDS.128 + STG.128, two integer ops, loop control).
+#pragma once
+#include "cr_common.cuh"
+
+namespace crb200 {
+
+__device__ __forceinline__ void cp_async16_u32(unsigned saddr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ int4 lds128_u32(unsigned saddr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+// Global units (UE elements each, contiguous) -> records.  Units are grouped GRP per record
+// (GRP = 1: one unit per record; GRP = 2: units 2t, 2t+1 are adjacent fields of record t).
+// Unit index k = kstart + j goes to record k / GRP, sub-field k % GRP.
+// `srec0` = shared address of the field in record 0, `nsb` = record stride in bytes.
+template <typename T, int UE, int GRP>
+__device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* __restrict__ g, int kstart, int nunits, bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if (nunits <= 0) return;
+  const int lane = threadIdx.x & 31;
+  if constexpr ((UE % VE) == 0) {
+    if (vec_ok) {
+      constexpr int CPU = UE / VE;          // chunks per unit
+      constexpr int CPR = CPU * GRP;        // chunks per record (for this field group)
+      const int total = nunits * CPU;
+      const char* gp = reinterpret_cast<const char*>(g) + lane * 16;
+      for (int i = lane; i < total; i += 32, gp += 512) {
+        const unsigned k = (unsigned)(i + kstart * CPU);
+        const unsigned rec = k / CPR, c = k - rec * CPR;
+        cp_async16_u32(srec0 + rec * nsb + c * 16, gp);
+      }
+      return;
+    }
+  }
+  constexpr int EPR = UE * GRP;
+  const int total = nunits * UE;
+  for (int i = lane; i < total; i += 32) {
+    const unsigned k = (unsigned)(i + kstart * UE);
+    const unsigned rec = k / EPR, c = k - rec * EPR;
+    T* dst = reinterpret_cast<T*>(__cvta_shared_to_generic(srec0 + rec * nsb)) + c;
+    cp_async_elem(dst, g + i);
+  }
+}
+
+// Records -> global units, same addressing.
+template <typename T, int UE, int GRP>
+__device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsigned nsb, int kstart, int nunits, bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if (nunits <= 0) return;
+  const int lane = threadIdx.x & 31;
+  if constexpr ((UE % VE) == 0) {
+    if (vec_ok) {
+      constexpr int CPU = UE / VE;
+      constexpr int CPR = CPU * GRP;
+      const int total = nunits * CPU;
+      char* gp = reinterpret_cast<char*>(g) + lane * 16;
+      for (int i = lane; i < total; i += 32, gp += 512) {
+        const unsigned k = (unsigned)(i + kstart * CPU);
+        const unsigned rec = k / CPR, c = k - rec * CPR;
+        *reinterpret_cast<int4*>(gp) = lds128_u32(srec0 + rec * nsb + c * 16);
+      }
+      return;
+    }
+  }
+  constexpr int EPR = UE * GRP;
+  const int total = nunits * UE;
+  for (int i = lane; i < total; i += 32) {
+    const unsigned k = (unsigned)(i + kstart * UE);
+    const unsigned rec = k / EPR, c = k - rec * EPR;
+    g[i] = reinterpret_cast<const T*>(__cvta_shared_to_generic(srec0 + rec * nsb))[c];
+  }
+}
+
+// compiler-only fence: stops the scheduler from hoisting later shared-memory loads above this
+// point (keeps the register live set of the fully unrolled row loops bounded)
+__device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+
+// record stride (elements): payload rounded up to an ODD number of 16-byte chunks, so that the
+// 8 lanes of a quarter warp hit 8 different 16-byte bank groups on per-thread vector accesses
+template <typename T>
+__host__ __device__ constexpr int record_stride(int payload_elems) {
+  return ((((payload_elems * (int)sizeof(T)) + 15) / 16) | 1) * 16 / (int)sizeof(T);
+}
+
+}  // namespace crb200

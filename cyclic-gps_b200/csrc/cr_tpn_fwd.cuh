@@ -1,0 +1,350 @@
+// Thread-per-node forward level kernel for small blocks (sizeof(T) * ell^2 <= 256 bytes).
+//
+// Same contract as cr_level_fwd_kernel (see cr_level_fwd.cuh for the maths and the reference
+// lines it replaces: cyclic_gps/cyclic_reduction.py:204-259, :412-427), different mapping:
+// ONE THREAD owns one even node and keeps K, F, G and the Schur products entirely in
+// registers, so there are no broadcast shared-memory reads and no shuffles inside the dense
+// algebra.  A CTA is a single warp: 31 owned even nodes + 1 read-only halo node whose
+// G G^T / G x contributions reach the neighbouring lane by __shfl_down.  Several such CTAs are
+// resident per SM (the kernel is limited by shared memory, ~1.3 KB per node at ell=8 fp32) and
+// overlap each other's load / compute / store phases.
+//
+// Shared memory holds one padded record per node,
+//     [ R_even | R_odd | O_left | O_right | O~ | y_even | y_odd ]   (stride NS, NS/16B odd)
+// filled by cp.async from three flat coalesced global ranges; results are written in place
+// (R_even->K, R_odd->R~, O_left->G, O_right->F, y_even->x, y_odd->y~) and leave as flat
+// coalesced ranges.  The odd record stride makes the per-thread 16-byte accesses conflict free.
+#pragma once
+#include "cr_common.cuh"
+#include "cr_level_fwd.cuh"
+#include "cr_tpn_common.cuh"
+
+namespace crb200 {
+
+template <typename T, int L>
+struct TpnFwdCfg {
+  static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= 256);
+  static constexpr int BS = L * L;
+  static constexpr int NT = 32, OWN = 31;
+  static constexpr int RE = 0, RO = BS, OL = 2 * BS, OR_ = 3 * BS, ON = 4 * BS, YE = 5 * BS, YO = 5 * BS + L;
+  static constexpr int RAW = 5 * BS + 2 * L;
+  static constexpr int NS = record_stride<T>(RAW);
+  static constexpr size_t SMEM = (size_t)NT * NS * sizeof(T);
+  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((220 * 1024) / (SMEM + 1024))));
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(32, TpnFwdCfg<T, L>::MIN_CTAS)
+cr_tpn_fwd_kernel(const LevelFwdArgs a) {
+  using C = TpnFwdCfg<T, L>;
+  constexpr int BS = C::BS, NS = C::NS, NT = C::NT, OWN = C::OWN;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* S = reinterpret_cast<T*>(smem_raw);
+  constexpr unsigned ES = sizeof(T);
+  const unsigned s0 = smem_u32(S);
+  const unsigned nsb = NS * ES;
+
+  const int m = a.m;
+  const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
+  const int tiles = (E + OWN - 1) / OWN;
+  const int b = blockIdx.x / tiles;
+  const int tile = blockIdx.x - b * tiles;
+  const int e0 = tile * OWN;
+  const bool has_y = a.y != nullptr;
+  const bool halo = a.O_halo != nullptr;
+  const int lane = threadIdx.x;
+
+  const T* gR = static_cast<const T*>(a.R) + (size_t)b * a.strideR;
+  const T* gO = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
+  const T* gy = has_y ? static_cast<const T*>(a.y) + (size_t)b * a.stridey : nullptr;
+
+  // ---------------- stage in ----------------
+  {
+    const int r0 = 2 * e0;
+    const int nR = cmin(2 * NT - 1, m - r0);
+    rec_g2s<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, nR, is_aligned16(gR));
+    const int pfirst = (r0 == 0) ? 1 : 0;
+    const int nO = cmin(2 * NT - 1, m - r0) - pfirst;
+    rec_g2s<T, BS, 2>(s0 + C::OL * ES, nsb, gO + (size_t)(r0 - 1 + pfirst) * BS, pfirst, nO, is_aligned16(gO));
+    if (r0 == 0 && halo)
+      rec_g2s<T, BS, 2>(s0 + C::OL * ES, nsb, static_cast<const T*>(a.O_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.O_halo));
+    if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
+    cp_async_wait_all();
+    __syncwarp();
+  }
+
+  // ---------------- per-node compute (everything in registers) ----------------
+  T* N = S + (size_t)lane * NS;
+  const int e = e0 + lane;
+  const bool valid = e < E;
+  const bool own = valid && (lane < OWN);
+  const bool do_f = own && (e < o);
+  const bool has_left = valid && (e >= 1 || halo);
+
+  T K[L][L];
+  T inv[L];
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+    T row[L];
+    lds_row<T, L>(row, N + C::RE + r * L);
+#pragma unroll
+    for (int c = 0; c < L; ++c) K[r][c] = valid ? row[c] : (r == c ? T(1) : T(0));
+  }
+  double dprod = 1.0;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const T d = K[k][k];
+    if (!(d > T(0))) bad = true;
+    const T lkk = sqrt(d);
+    inv[k] = T(1) / lkk;
+    K[k][k] = lkk;
+    dprod *= (double)lkk;
+#pragma unroll
+    for (int r = k + 1; r < L; ++r) K[r][k] *= inv[k];
+#pragma unroll
+    for (int c = k + 1; c < L; ++c)
+#pragma unroll
+      for (int r = c; r < L; ++r) K[r][c] = fma(-K[r][k], K[c][k], K[r][c]);
+  }
+  if (valid) {
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T row[L];
+#pragma unroll
+      for (int c = 0; c < L; ++c) row[c] = (c <= r) ? K[r][c] : T(0);
+      sts_row<T, L>(N + C::RE + r * L, row);
+    }
+  }
+  if (bad && own && a.info != nullptr) {
+    const long long flat = (long long)b * E + e;
+    atomicMax(a.info, 0x7fffffff - (int)(flat > 0x7ffffffeLL ? 0x7ffffffeLL : flat));
+  }
+  double ld_part = (own && a.logdet != nullptr) ? log(dprod) : 0.0;
+
+  // x = K^{-1} y_even
+  T x[L];
+  double mh_part = 0.0;
+#pragma unroll
+  for (int c = 0; c < L; ++c) x[c] = T(0);
+  if (has_y) {
+    if (valid) lds_row<T, L>(x, N + C::YE);
+#pragma unroll
+    for (int c = 0; c < L; ++c) {
+      T s = x[c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) s = fma(-x[k], K[c][k], s);
+      x[c] = s * inv[c];
+    }
+    if (!valid) {
+#pragma unroll
+      for (int c = 0; c < L; ++c) x[c] = T(0);
+    }
+    if (valid) sts_row<T, L>(N + C::YE, x);
+    if (own) {
+#pragma unroll
+      for (int c = 0; c < L; ++c) mh_part += (double)x[c] * (double)x[c];
+    }
+  }
+
+  // F = O_right K^{-T} (row by row), A = F F^T (lower), u = F x
+  T A[L][L];   // only r >= c used
+  T u[L];
+  {
+    T F[L][L];
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T f[L];
+      lds_row<T, L>(f, N + C::OR_ + r * L);
+#pragma unroll
+      for (int c = 0; c < L; ++c) {
+        T s = do_f ? f[c] : T(0);
+#pragma unroll
+        for (int k = 0; k < c; ++k) s = fma(-f[k], K[c][k], s);
+        f[c] = s * inv[c];
+      }
+      if (do_f) sts_row<T, L>(N + C::OR_ + r * L, f);
+      T ur = T(0);
+#pragma unroll
+      for (int c = 0; c < L; ++c) { F[r][c] = f[c]; ur = fma(f[c], x[c], ur); }
+      u[r] = ur;
+    }
+#pragma unroll
+    for (int r = 0; r < L; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < L; ++k) s = fma(F[r][k], F[c][k], s);
+        A[r][c] = s;
+      }
+  }
+
+  // G = O_left^T K^{-T}: row r of G solves against column r of O_left
+  T G[L][L];
+  {
+#pragma unroll
+    for (int c = 0; c < L; ++c) {
+      T row[L];
+      lds_row<T, L>(row, N + C::OL + c * L);
+#pragma unroll
+      for (int r = 0; r < L; ++r) G[r][c] = has_left ? row[r] : T(0);
+    }
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+#pragma unroll
+      for (int c = 0; c < L; ++c) {
+        T s = G[r][c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s = fma(-G[r][k], K[c][k], s);
+        G[r][c] = s * inv[c];
+      }
+    }
+    if (has_left) {
+#pragma unroll
+      for (int r = 0; r < L; ++r) sts_row<T, L>(N + C::OL + r * L, G[r]);
+    }
+  }
+
+  // O~_{e-1} = -F G^T (F rows re-read from shared memory), B = G G^T (lower), v = G x
+  if (do_f && has_left) {
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T f[L], on[L];
+      lds_row<T, L>(f, N + C::OR_ + r * L);
+#pragma unroll
+      for (int c = 0; c < L; ++c) {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < L; ++k) s = fma(-f[k], G[c][k], s);
+        on[c] = s;
+      }
+      sts_row<T, L>(N + C::ON + r * L, on);
+    }
+  }
+  T Bn[L][L];   // lower: G G^T of the NEXT even node after the shuffle
+  T vn[L];
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+#pragma unroll
+    for (int c = 0; c <= r; ++c) {
+      T s = T(0);
+#pragma unroll
+      for (int k = 0; k < L; ++k) s = fma(G[r][k], G[c][k], s);
+      Bn[r][c] = s;
+    }
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < L; ++k) s = fma(G[r][k], x[k], s);
+    vn[r] = s;
+  }
+  if (halo && e0 == 0 && lane == 0) {
+    // link to the virtual node -1: accumulate -G G^T and -G x there
+    if (a.Rh_acc != nullptr) {
+      T* acc = static_cast<T*>(a.Rh_acc) + (size_t)b * BS;
+#pragma unroll
+      for (int r = 0; r < L; ++r)
+#pragma unroll
+        for (int c = 0; c < L; ++c) acc[r * L + c] -= (r >= c) ? Bn[r][c] : Bn[c][r];
+    }
+    if (a.yh_acc != nullptr && has_y) {
+      T* acc = static_cast<T*>(a.yh_acc) + (size_t)b * L;
+#pragma unroll
+      for (int r = 0; r < L; ++r) acc[r] -= vn[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+#pragma unroll
+    for (int c = 0; c <= r; ++c) Bn[r][c] = __shfl_down_sync(0xffffffffu, Bn[r][c], 1);
+    vn[r] = __shfl_down_sync(0xffffffffu, vn[r], 1);
+  }
+
+  // R~_e = R_odd - A - B_{e+1},  y~_e = y_odd - u - v_{e+1}
+  if (do_f) {
+    const bool next_even = (e + 1) < E;
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T row[L];
+      lds_row<T, L>(row, N + C::RO + r * L);
+#pragma unroll
+      for (int c = 0; c < L; ++c) {
+        const T av = (r >= c) ? A[r][c] : A[c][r];
+        const T bv = (r >= c) ? Bn[r][c] : Bn[c][r];
+        row[c] = row[c] - av - (next_even ? bv : T(0));
+      }
+      sts_row<T, L>(N + C::RO + r * L, row);
+    }
+    if (has_y) {
+      T yo[L];
+      lds_row<T, L>(yo, N + C::YO);
+#pragma unroll
+      for (int r = 0; r < L; ++r) yo[r] = yo[r] - u[r] - (next_even ? vn[r] : T(0));
+      sts_row<T, L>(N + C::YO, yo);
+    }
+  }
+
+  // scalars: warp reduce, one atomic per CTA
+  if (a.logdet != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ld_part += __shfl_xor_sync(0xffffffffu, ld_part, off);
+    if (lane == 0) atomicAdd(a.logdet + b, ld_part);
+  }
+  if (a.mahal != nullptr && has_y) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mh_part += __shfl_xor_sync(0xffffffffu, mh_part, off);
+    if (lane == 0) atomicAdd(a.mahal + b, mh_part);
+  }
+  __syncwarp();
+
+  // ---------------- stage out ----------------
+  const int n_own = cmin(OWN, E - e0);
+  const int n_odd = cmax(0, cmin(OWN, o - e0));
+  if (a.D != nullptr) {
+    rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+    rec_s2g<T, BS, 1>(static_cast<T*>(a.F) + ((size_t)b * o + e0) * BS, s0 + C::OR_ * ES, nsb, 0, n_odd, is_aligned16(a.F));
+    const int gfirst = (e0 == 0) ? 1 : 0;
+    rec_s2g<T, BS, 1>(static_cast<T*>(a.G) + ((size_t)b * gcnt + (e0 + gfirst - 1)) * BS, s0 + C::OL * ES, nsb, gfirst, n_own - gfirst,
+                      is_aligned16(a.G));
+  }
+  if (a.xk != nullptr && has_y)
+    rec_s2g<T, L, 1>(static_cast<T*>(a.xk) + ((size_t)b * E + e0) * L, s0 + C::YE * ES, nsb, 0, n_own, is_aligned16(a.xk));
+  if (a.Rn != nullptr && n_odd > 0) {
+    rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RO * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+    if (has_y && a.yn != nullptr)
+      rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
+    const int ofirst = (e0 == 0) ? 1 : 0;
+    const int n_on = cmax(0, cmin(e0 + n_own, o) - (e0 + ofirst));
+    if (a.On != nullptr && n_on > 0)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.On) + ((size_t)b * (o - 1) + (e0 + ofirst - 1)) * BS, s0 + C::ON * ES, nsb, ofirst, n_on,
+                        is_aligned16(a.On));
+  }
+  if (halo && e0 == 0) {
+    if (a.G_halo != nullptr)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.G_halo) + (size_t)b * BS, s0 + C::OL * ES, nsb, 0, 1, is_aligned16(a.G_halo));
+    if (a.On_halo != nullptr && o > 0)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.On_halo) + (size_t)b * BS, s0 + C::ON * ES, nsb, 0, 1, is_aligned16(a.On_halo));
+  }
+}
+
+template <typename T, int L>
+cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
+  using C = TpnFwdCfg<T, L>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(cr_tpn_fwd_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  const int E = (a.m + 1) / 2;
+  const long long tiles = (E + C::OWN - 1) / C::OWN;
+  const long long grid = tiles * a.batch;
+  if (grid <= 0) return cudaSuccess;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  cr_tpn_fwd_kernel<T, L><<<(unsigned)grid, 32, C::SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace crb200

@@ -28,7 +28,7 @@ class FwdArgs(C.Structure):
                 ("D", _vp), ("F", _vp), ("G", _vp), ("xk", _vp),
                 ("Rn", _vp), ("On", _vp), ("yn", _vp),
                 ("logdet", _vp), ("mahal", _vp), ("info", _vp),
-                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp)]
+                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp), ("variant", _i)]
 
 
 class BwdArgs(C.Structure):
@@ -38,7 +38,7 @@ class BwdArgs(C.Structure):
                 ("Sd_out", _vp), ("So_out", _vp), ("w_out", _vp),
                 ("strideSd", _ll), ("strideSo", _ll), ("stridew", _ll),
                 ("gm", _vp), ("gd", _vp), ("grad_mode", _i),
-                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp), ("So_halo_out", _vp)]
+                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp), ("So_halo_out", _vp), ("variant", _i)]
 
 
 class HsArgs(C.Structure):
@@ -128,6 +128,9 @@ def _fill(struct, fields):
     return struct
 
 
+# Kernel family override for tests / benchmarks: 0 auto, 1 lane-per-row, 2 thread-per-node.
+VARIANT = int(os.environ.get("CRB200_VARIANT", "0"))
+
 # Optional launch tracer (bench.py): an object with begin(kind, dtype, ell, batch, m) -> token
 # and end(token); called around every native launch on the current stream.
 TRACE = None
@@ -143,10 +146,12 @@ def _traced(kind, fn, dtype, ell, a):
 
 
 def level_fwd(dtype: torch.dtype, ell: int, **fields):
+    fields.setdefault("variant", VARIANT)
     _traced("fwd", load().crb200_level_fwd, dtype, ell, _fill(FwdArgs(), fields))
 
 
 def level_bwd(dtype: torch.dtype, ell: int, **fields):
+    fields.setdefault("variant", VARIANT)
     _traced("bwd", load().crb200_level_bwd, dtype, ell, _fill(BwdArgs(), fields))
 
 

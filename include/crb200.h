@@ -29,6 +29,11 @@ extern "C" {
 #define CRB200_F32 0
 #define CRB200_F64 1
 
+/* kernel families: lane-per-row (any ell <= 32) and thread-per-node (sizeof(T)*ell*ell <= 256 B) */
+#define CRB200_AUTO 0
+#define CRB200_LANE_PER_ROW 1
+#define CRB200_THREAD_PER_NODE 2
+
 #define CRB200_OK 0
 #define CRB200_EINVAL (-1)        /* null / inconsistent argument                      */
 #define CRB200_EUNSUPPORTED (-2)  /* ell or dtype outside the compiled range           */
@@ -50,6 +55,7 @@ typedef struct crb200_fwd_args {
                                                          caller zero-initialises; 0 = all blocks PD  */
   /* left halo (chunk-partitioned series): virtual surviving node -1 coupled to row 0 by O_halo */
   const void* O_halo; void* G_halo; void* On_halo; void* Rh_acc; void* yh_acc;   /* (batch,l,l)x4, (batch,l) */
+  int variant;                                        /* CRB200_AUTO, or force one kernel family (tests, benchmarks) */
 } crb200_fwd_args;
 
 /* One CR level, backward direction (deepest level first).  Replaces the per-level bodies of
@@ -67,6 +73,7 @@ typedef struct crb200_bwd_args {
   const double* gm; const double* gd;                            /* per-series cotangents (grad_mode)  */
   int grad_mode;                                                 /* 0: Sigma / w ; 1: gR / gO / gx     */
   const void* G_halo; const void* Sd_halo; const void* w_halo; const void* So_halo_in; void* So_halo_out;
+  int variant;
 } crb200_bwd_args;
 
 /* Half solve against stored factors.  Replaces one iteration of halfsolve (:318-333):

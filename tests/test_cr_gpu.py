@@ -98,11 +98,15 @@ def _check_golden_case(g, p, tol):
         assert_close(xr.grad, g[p + "gx_" + tag], tol, p + "gx " + tag)
 
 
-def test_golden_leg(golden):
-    g = golden["leg"]
-    for p in g["cases"]:
-        p = str(p)
-        _check_golden_case(g, p, 1e-4 if "float32" in p else 1e-10)
+def _golden_cases(name):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    return [str(c) for c in np.load(path)["cases"]]
+
+
+@pytest.mark.parametrize("case", _golden_cases("leg"))
+def test_golden_leg(golden, case):
+    _check_golden_case(golden["leg"], case, 1e-4 if "float32" in case else 1e-10)
 
 
 def test_golden_random_llt(golden):
