@@ -43,6 +43,32 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+def _unit_key(cmd):
+    """Hash of the preprocessed translation unit (line markers stripped) + the command line:
+    an object is rebuilt only when something it actually includes has changed."""
+    pre = [c for c in cmd if c not in ("-c",)]
+    o = pre.index("-o")
+    pre = pre[:o] + pre[o + 2:] + ["-E"]
+    r = subprocess.run(pre, capture_output=True, text=True)
+    if r.returncode != 0:
+        return None
+    body = "\n".join(l for l in r.stdout.splitlines() if l.strip() and not l.startswith("#"))
+    return hashlib.sha256((" ".join(cmd[1:]) + body).encode()).hexdigest()[:20]
+
+
+def _compile_unit(unit, verbose=False):
+    obj, cmd = unit
+    key = _unit_key(cmd)
+    keyfile = obj + ".key"
+    if key is not None and os.path.exists(obj) and os.path.exists(keyfile) and open(keyfile).read().strip() == key:
+        return ""
+    out = _run(cmd)
+    if key is not None:
+        with open(keyfile, "w") as fh:
+            fh.write(key)
+    return out
+
+
 def _run(cmd):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -60,6 +86,7 @@ def build(force=False, jobs=None, verbose=False, only=None):
     stub that reports cudaErrorNotSupported (never leaves a `current` stamp behind)."""
     if not force and only is None and is_current():
         return OUT
+    tag = source_hash()       # taken BEFORE compiling: edits made during the build must not be stamped
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     units = []
@@ -75,12 +102,12 @@ def build(force=False, jobs=None, verbose=False, only=None):
     # longest units (large ell) first
     units.sort(key=lambda u: -int(u[0].rsplit("_", 1)[-1].split(".")[0]) if "inst_" in u[0] else 0)
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
-        for out in ex.map(lambda u: _run(u[1]), units):
+        for out in ex.map((lambda u: _run(u[1])) if force else _compile_unit, units):
             if verbose and out.strip():
                 print(out)
     _run([nvcc, "-shared", "-o", OUT] + [u[0] for u in units] + ["-lcudart"])
     with open(STAMP, "w") as fh:
-        fh.write(source_hash() if only is None else "partial:" + only)
+        fh.write(tag if only is None else "partial:" + only)
     return OUT
 
 

@@ -2,8 +2,13 @@
 // in parallel.  -DCRB_T=float|double -DCRB_TN=f32|f64 -DCRB_LO=.. -DCRB_HI=..
 #include "cr_level_fwd.cuh"
 #include "cr_level_bwd.cuh"
+#if CRB_LO <= 8   // thread-per-node kernels exist only where sizeof(T) * ell^2 <= 256 bytes
 #include "cr_tpn_fwd.cuh"
 #include "cr_tpn_bwd.cuh"
+#define CRB_HAVE_TPN 1
+#else
+#define CRB_HAVE_TPN 0
+#endif
 #include "cr_halfsolve.cuh"
 
 #define CRB_CAT_(a, b, c, d) a##_##b##_##c##_##d
@@ -24,9 +29,12 @@ template <int L>
 struct Dispatch {
   static cudaError_t fwd(int ell, const LevelFwdArgs& a, cudaStream_t s) {
     if (ell == L) {
+#if CRB_HAVE_TPN
       if constexpr (TpnFwdCfg<CRB_T, L>::ELIGIBLE) {
         if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_fwd<CRB_T, L>(a, s);
-      } else {
+      } else
+#endif
+      {
         if (a.variant == CRB200_THREAD_PER_NODE) return cudaErrorInvalidValue;
       }
       return launch_level_fwd<CRB_T, L>(a, s);
@@ -35,9 +43,12 @@ struct Dispatch {
   }
   static cudaError_t bwd(int ell, const LevelBwdArgs& a, cudaStream_t s) {
     if (ell == L) {
+#if CRB_HAVE_TPN
       if constexpr (TpnBwdCfg<CRB_T, L>::ELIGIBLE) {
         if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_bwd<CRB_T, L>(a, s);
-      } else {
+      } else
+#endif
+      {
         if (a.variant == CRB200_THREAD_PER_NODE) return cudaErrorInvalidValue;
       }
       return launch_level_bwd<CRB_T, L>(a, s);
@@ -50,11 +61,17 @@ struct Dispatch {
   }
   static int fwd_tile(int ell) {
     if (ell != L) return Dispatch<L + 1>::fwd_tile(ell);
-    return TpnFwdCfg<CRB_T, L>::ELIGIBLE ? TpnFwdCfg<CRB_T, L>::OWN : FwdCfg<CRB_T, L>::NG - 1;
+#if CRB_HAVE_TPN
+    if (TpnFwdCfg<CRB_T, L>::ELIGIBLE) return TpnFwdCfg<CRB_T, L>::OWN;
+#endif
+    return FwdCfg<CRB_T, L>::NG - 1;
   }
   static int bwd_tile(int ell) {
     if (ell != L) return Dispatch<L + 1>::bwd_tile(ell);
-    return TpnBwdCfg<CRB_T, L>::ELIGIBLE ? TpnBwdCfg<CRB_T, L>::NT : BwdCfg<CRB_T, L>::NG;
+#if CRB_HAVE_TPN
+    if (TpnBwdCfg<CRB_T, L>::ELIGIBLE) return TpnBwdCfg<CRB_T, L>::NT;
+#endif
+    return BwdCfg<CRB_T, L>::NG;
   }
 };
 template <>

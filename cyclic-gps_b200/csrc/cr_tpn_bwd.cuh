@@ -276,9 +276,12 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   }
 
   if (do_sigma) {
+    // The three big products run as ROLLED loops over a row / column index that only addresses
+    // shared memory (P and Q keep static register indices): 8x less code than full unrolling, which
+    // matters because five single-warp CTAs at different program counters share one SM's i-cache.
     // Sigma_{2e+1,2e} = -(S~_d[e] P + S~_o[e-1] Q), row by row into B
     if (has_odd) {
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < L; ++r) {
         T sig[L], so[L], out[L];
         lds_row<T, L>(sig, N + Cf::SD + r * L);
@@ -291,22 +294,58 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
           out[c] = s;
         }
         sts_row<T, L>(N + Cf::B + r * L, out);
-        sched_fence();
       }
     }
-    // Sigma_{2e,2e-1} and Sigma_{2e,2e}: row ranges [0,H) and [H,L) separately to bound the live registers
-    constexpr int H = (L + 1) / 2;
+    // Sigma_{2e,2e-1} = -(Q^T S~_d[e-1]^T + P^T S~_o[e-1]), COLUMN by column into C:
+    // column c needs row c of S~_d[e-1] (left record) and column c of S~_o[e-1]
     if (has_left) {
-      tpn_bwd_so_rows<T, L, 0, H>(P, Q, Lf + Cf::SD, N + Cf::SO, N + Cf::C, has_so);
-      tpn_bwd_so_rows<T, L, H, L>(P, Q, Lf + Cf::SD, N + Cf::SO, N + Cf::C, has_so);
+#pragma unroll 1
+      for (int c = 0; c < L; ++c) {
+        T a0[L], socol[L], st[L];
+        lds_row<T, L>(a0, Lf + Cf::SD + c * L);
+#pragma unroll
+        for (int k = 0; k < L; ++k) socol[k] = has_so ? N[Cf::SO + k * L + c] : T(0);
+#pragma unroll
+        for (int r = 0; r < L; ++r) {
+          T s = T(0);
+#pragma unroll
+          for (int k = 0; k < L; ++k) { s = fma(-Q[k][r], a0[k], s); s = fma(-P[k][r], socol[k], s); }
+          st[r] = s;
+        }
+#pragma unroll
+        for (int r = 0; r < L; ++r) N[Cf::C + r * L + c] = st[r];
+      }
     }
+    // Sigma_{2e,2e} = Di^T Di - S_d^T P - (S_o^T) Q, row by row in place in A:
+    // row r needs column r of S_d (B) and row r of Sigma_{2e,2e-1} (C)
     if (valid) {
       T wv[L];
 #pragma unroll
       for (int c = 0; c < L; ++c) wv[c] = T(0);
       if (grad && do_w) lds_row<T, L>(wv, N + Cf::X);
-      tpn_bwd_se_rows<T, L, 0, H>(P, Q, N + Cf::A, N + Cf::B, N + Cf::C, has_odd, has_left, grad, gd, gm, wv);
-      tpn_bwd_se_rows<T, L, H, L>(P, Q, N + Cf::A, N + Cf::B, N + Cf::C, has_odd, has_left, grad, gd, gm, wv);
+#pragma unroll 1
+      for (int r = 0; r < L; ++r) {
+        T acc[L], sdcol[L], st[L];
+        lds_row<T, L>(acc, N + Cf::A + r * L);
+        lds_row<T, L>(st, N + Cf::C + r * L);
+#pragma unroll
+        for (int k = 0; k < L; ++k) sdcol[k] = has_odd ? N[Cf::B + k * L + r] : T(0);
+#pragma unroll
+        for (int c = 0; c < L; ++c) {
+          T s = acc[c];
+#pragma unroll
+          for (int k = 0; k < L; ++k) { s = fma(-sdcol[k], P[k][c], s); s = fma(has_left ? -st[k] : T(0), Q[k][c], s); }
+          acc[c] = s;
+        }
+        if (grad) {
+          T wr = T(0);
+#pragma unroll
+          for (int c = 0; c < L; ++c) wr = (c == r) ? wv[c] : wr;
+#pragma unroll
+          for (int c = 0; c < L; ++c) acc[c] = gd * acc[c] - gm * wr * wv[c];
+        }
+        sts_row<T, L>(N + Cf::A + r * L, acc);
+      }
     }
   }
   __syncwarp();   // neighbours are done reading this record's SD / WT

@@ -92,6 +92,15 @@ def _alloc_levels(total_rows: Sequence[int], trailing, batch, dtype, device):
     return flat, views
 
 
+def _rows_contiguous(t):
+    """The kernels take an arbitrary series (batch) stride but need every series' rows back to
+    back; anything else is copied."""
+    if t is None or t.numel() == 0:
+        return t
+    inner = t[0]
+    return t if inner.is_contiguous() else t.contiguous()
+
+
 def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *, keep_factors: bool,
                   want_logdet: bool = True, nlevels: Optional[int] = None,
                   halo_O: Optional[torch.Tensor] = None) -> FactorPack:
@@ -100,6 +109,7 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
     R (B,n,l,l), O (B,n-1,l,l) [any strided batch axis, rows contiguous], y (B,n,l) or None."""
     B, n, ell = R.shape[0], R.shape[1], R.shape[2]
     dtype, dev = R.dtype, R.device
+    R, O, y = _rows_contiguous(R), _rows_contiguous(O), _rows_contiguous(y)
     ms_all = level_sizes(n)
     L = len(ms_all) if nlevels is None else min(nlevels, len(ms_all))
     ms = ms_all[:L]

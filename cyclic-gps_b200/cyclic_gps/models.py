@@ -1,0 +1,167 @@
+"""LEG model glue with the reference's class and method names (cyclic_gps/models.py), kept
+to what calls the CR hot path: parameters -> G -> block-tridiagonal precision (Rs, Os) ->
+``decompose`` / ``det`` / ``mahal_and_det`` / ``solve`` / ``inverse_blocks`` from
+``cyclic_gps.cyclic_reduction`` (the B200 engine).  The prediction helpers of the reference
+(forecast / interpolate / intercast / make_predictions, models.py:394-546) are outside the
+hot path and not provided.  ``pytorch_lightning`` is optional: without it the class is a plain
+``torch.nn.Module`` with the same training_step / configure_optimizers hooks."""
+import math
+
+import torch
+from torch.optim import LBFGS, Adam
+from torch.optim.lr_scheduler import ReduceLROnPlateau
+
+from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_and_det, solve
+
+try:  # pragma: no cover - not installed in the build image
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # noqa: BLE001
+    class _Base(torch.nn.Module):
+        def log(self, *args, **kwargs):
+            return None
+
+
+class LEGFamily(_Base):
+    r"""z ~ PEG(N, R),  x(t) ~ N(B z(t), Lambda Lambda^T)   (reference models.py:20-27)."""
+
+    def __init__(self, rank: int, obs_dim: int, prior_process_noise_level: float = 1.0, prior_length_scale: float = 0.2,
+                 train: bool = False, optimizer: str = "ADAM", data_type=torch.float32, lr=1e-2) -> None:
+        super().__init__()
+        self.rank, self.obs_dim = rank, obs_dim
+        self.prior_process_noise_level = prior_process_noise_level
+        self.prior_length_scale = prior_length_scale
+        self.optimizer, self.data_type, self.lr = optimizer, data_type, lr
+        tri = lambda n, off: self.inds_to_tuple(torch.tril_indices(row=n, col=n, offset=off))
+        self.N_idxs, self.R_idxs, self.Lambda_idxs = tri(rank, 0), tri(rank, -1), tri(obs_dim, 0)
+        par = lambda k: torch.nn.Parameter(torch.zeros(k, dtype=data_type), requires_grad=train)
+        self.N_params, self.R_params = par(len(self.N_idxs[0])), par(len(self.R_idxs[0]))
+        self.Lambda_params = par(len(self.Lambda_idxs[0]))
+        self.B = torch.nn.Parameter(torch.zeros((obs_dim, rank), dtype=data_type), requires_grad=train)
+        self.get_initial_guess()
+        self.register_model_matrices_from_params()
+
+    @staticmethod
+    def inds_to_tuple(raw_inds):
+        return (raw_inds[0], raw_inds[1])
+
+    # ---- initial values (reference models.py:81-121)
+    def get_initial_guess(self):
+        self.set_initial_N()
+        self.set_initial_R()
+        self.set_initial_B()
+        self.set_initial_Lambda()
+
+    def set_initial_N(self):
+        N = torch.eye(self.rank, dtype=self.data_type) * self.prior_process_noise_level
+        self.N_params.data = torch.linalg.cholesky(N @ N.T)[self.N_idxs]
+
+    def set_initial_R(self):
+        A = torch.randn((self.rank, self.rank), dtype=self.data_type)
+        self.R_params.data = ((A - A.T) * self.prior_length_scale)[self.R_idxs]
+
+    def set_initial_Lambda(self):
+        Lam = 0.1 * torch.eye(self.obs_dim, dtype=self.data_type)
+        self.Lambda_params.data = torch.linalg.cholesky(Lam @ Lam.T)[self.Lambda_idxs]
+
+    def set_initial_B(self):
+        ones = torch.ones((self.obs_dim, self.rank), dtype=self.data_type)
+        self.B.data = 0.5 * ones / torch.sqrt(torch.sum(ones ** 2, dim=1, keepdim=True))
+
+    @property
+    def parameter_count(self) -> int:
+        return len(self.N_params) + len(self.R_params) + len(self.Lambda_params) + torch.numel(self.B)
+
+    # ---- parameters -> matrices (reference models.py:135-178)
+    def _scatter(self, n, idxs, values):
+        M = torch.zeros(n, n, dtype=values.dtype, device=values.device)
+        M[idxs] = values
+        return M
+
+    def N_from_params(self):
+        self.register_buffer("N", self._scatter(self.rank, self.N_idxs, self.N_params))
+
+    def R_from_params(self):
+        self.register_buffer("R", self._scatter(self.rank, self.R_idxs, self.R_params))
+
+    def Lambda_from_params(self):
+        self.register_buffer("Lambda", self._scatter(self.obs_dim, self.Lambda_idxs, torch.nn.functional.softplus(self.Lambda_params)))
+
+    def calc_G(self):
+        eye = torch.eye(self.rank, dtype=self.N.dtype, device=self.N.device)
+        self.register_buffer("G", self.N @ self.N.T + self.R - self.R.T + 1e-5 * eye)
+
+    @staticmethod
+    def calc_Lambda_Lambda_T(Lambda):
+        if Lambda.dim() == 2:
+            return Lambda @ Lambda.T + 1e-9 * torch.eye(Lambda.shape[0], dtype=Lambda.dtype, device=Lambda.device)
+        return torch.diag(Lambda ** 2 + 1e-9)
+
+    def register_model_matrices_from_params(self):
+        self.Lambda_from_params()
+        self.N_from_params()
+        self.R_from_params()
+        self.calc_G()
+
+    # ---- precision blocks (reference models.py:181-239, 254-280)
+    def compute_PEG_precision(self, ts):
+        """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision."""
+        gaps = ts[1:] - ts[:-1]
+        eye = torch.eye(self.rank, dtype=self.G.dtype, device=self.G.device)
+        A = torch.matrix_exp(-0.5 * self.G.unsqueeze(0) * gaps.reshape(-1, 1, 1))
+        At = A.transpose(1, 2)
+        fwd = torch.linalg.solve(eye - A @ At, A)            # (I - A A^T)^{-1} A
+        bwd = torch.linalg.solve(eye - At @ A, At)           # (I - A^T A)^{-1} A^T
+        from_prev, to_next = A @ bwd, At @ fwd
+        diag = torch.cat([(eye + to_next[0]).unsqueeze(0), eye + from_prev[:-1] + to_next[1:], (eye + from_prev[-1]).unsqueeze(0)], dim=0)
+        return diag, -fwd
+
+    def _obs_terms(self):
+        LLT = self.calc_Lambda_Lambda_T(self.Lambda)
+        return LLT, self.B.T @ torch.linalg.solve(LLT, self.B)
+
+    def compute_posterior_precision(self, ts):
+        _, shift = self._obs_terms()
+        Rs, Os = self.compute_PEG_precision(ts)
+        return Rs + shift.unsqueeze(0), Os
+
+    def compute_v(self, xs):
+        LLT = self.calc_Lambda_Lambda_T(self.Lambda)
+        return torch.linalg.solve(LLT, xs.T).T @ self.B
+
+    def compute_insample_posterior(self, ts, xs):
+        """Posterior mean (n,l) and {"Rs","Os"} blocks of the posterior covariance
+        (reference models.py:282-298)."""
+        K = {}
+        K["Rs"], K["Os"] = self.compute_posterior_precision(ts)
+        dec = decompose(**K)
+        mean = solve(dec, self.compute_v(xs))
+        cov = {}
+        cov["Rs"], cov["Os"] = inverse_blocks(dec)
+        return mean, cov
+
+    def log_likelihood(self, ts, xs):
+        """log p(xs | ts) through two CR factorisations (reference models.py:301-372)."""
+        self.register_model_matrices_from_params()
+        LLT, shift = self._obs_terms()
+        white = torch.linalg.solve(LLT, xs.T).T
+        obs_mahal = torch.sum(white * xs)
+        obs_logdet = torch.logdet(2 * math.pi * LLT) * xs.shape[0]
+        v = white @ self.B
+        Rs, Os = self.compute_PEG_precision(ts)
+        prior_logdet = det(decompose(Rs, Os))
+        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift.unsqueeze(0), Os=Os, x=v)
+        return -0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))
+
+    # ---- training hooks (reference models.py:374-392)
+    def training_step(self, train_batch, batch_idx):
+        t, x = train_batch
+        nobs = x.shape[0] * x.shape[1] * x.shape[2]
+        loss = -self.log_likelihood(t.squeeze(0), x.squeeze(0)) / nobs
+        self.log("NLL", loss)
+        return loss
+
+    def configure_optimizers(self):
+        params = [p for p in self.parameters() if p.requires_grad]
+        opt = Adam(params, lr=self.lr) if self.optimizer == "ADAM" else LBFGS(params, lr=self.lr, max_iter=20)
+        return {"optimizer": opt, "lr_scheduler": ReduceLROnPlateau(opt, "min"), "monitor": "NLL"}

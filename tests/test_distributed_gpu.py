@@ -1,0 +1,81 @@
+"""GPU: the chunk-partitioned long-series path on the real CUDA engine (left-halo kernels,
+boundary system, descent) against the unchunked oracle; world=1 in process and world=2 as two
+processes sharing cuda:0 over gloo (the all-gather payload is < 1 kB per rank, so the transport
+does not matter for correctness; NCCL is used by bench.py on real multi-GPU runs)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, os.path.join(ROOT, "cyclic-gps_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from helpers import TOL, assert_close  # noqa: E402
+from oracle import cr_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _series(n, l, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    G, B, LLT = orc.leg_params(l, seed=seed)
+    gaps = -torch.log(torch.rand(n - 1, generator=g, dtype=torch.float64)) + 0.05
+    R, O = orc.leg_posterior_precision(gaps, G, B, LLT)
+    x = torch.randn((n, l), generator=g, dtype=torch.float64)
+    Oprev = torch.cat([torch.full((1, l, l), 3.0, dtype=torch.float64), O], dim=0)
+    return R.to(dtype), O.to(dtype), Oprev.to(dtype), x.to(dtype)
+
+
+def _run(rank, world, n, l, dtype, sub, group=None, variant=0):
+    from cyclic_gps import _native, distributed as D
+    _native.VARIANT = variant
+    R, O, Oprev, x = _series(n, l, dtype, seed=n + l)
+    plan = D.make_plan(n, world, sub=sub)
+    lo, hi = plan.rows(rank)
+    Rl = R[lo:hi].cuda().requires_grad_(True)
+    Ol = Oprev[lo:hi].cuda().requires_grad_(True)
+    xl = x[lo:hi].cuda().requires_grad_(True)
+    mh, ld = D.chunked_mahal_and_det(Rl, Ol, xl, plan, rank, group=group)
+    (0.8 * mh - 0.6 * ld).backward()
+    tol = TOL[dtype]
+    Rd, Od, xd = R.double(), O.double(), x.double()
+    dec = orc.factor(Rd, Od)
+    assert_close(mh, orc.mahal(dec, xd), tol, "mahal")
+    assert_close(ld, orc.logdet(dec), tol, "logdet")
+    gR, gO, gx = orc.loglik_grads(Rd, Od, xd, 0.8, -0.6)
+    gOprev = torch.cat([torch.zeros(1, l, l, dtype=torch.float64), gO], dim=0)
+    assert_close(Rl.grad, gR[lo:hi], tol, "gR")
+    assert_close(Ol.grad, gOprev[lo:hi], tol, "gOprev")
+    assert_close(xl.grad, gx[lo:hi], tol, "gx")
+    _native.VARIANT = 0
+
+
+@pytest.mark.parametrize("n,l,dtype,sub,variant", [
+    (5000, 4, torch.float32, 256, 0), (4096, 8, torch.float32, 512, 0), (3001, 3, torch.float64, 128, 0),
+    (2050, 2, torch.float64, 64, 0), (1000, 8, torch.float64, 64, 0), (777, 16, torch.float64, 32, 0),
+    (3001, 3, torch.float64, 128, 1), (1500, 8, torch.float32, 128, 1)])
+def test_chunked_world1(n, l, dtype, sub, variant):
+    _run(0, 1, n, l, dtype, sub, variant=variant)
+
+
+def _worker(rank, world, port):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        _run(rank, world, 6000, 4, torch.float32, 256)
+        _run(rank, world, 2500, 3, torch.float64, 128)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunked_world2_shared_gpu():
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
