@@ -189,6 +189,111 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_long(args):
+    """BASELINE configs[3]: ONE series of n rows (default 1e8), l = 4, fp32, rows spread over the ranks
+    (chunk-partitioned CR, cyclic_gps.distributed); strong scaling.  step = loglik forward + backward."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from cyclic_gps import _native, distributed as D
+    from cyclic_gps.synth import gaps_for_rows, leg_params, leg_precision_rows
+    _native.load()
+    n, ell = args.n, args.ell
+    dtype = getattr(torch, args.dtype)
+    s = torch.empty((), dtype=dtype).element_size()
+    plan = D.make_plan(n, world, sub=args.sub)
+    lo, hi = plan.rows(rank)
+    G, Bm, LLT = leg_params(ell, seed=0, device=dev)
+    R, Oprev = leg_precision_rows(gaps_for_rows(lo, hi, n, seed=7, device=dev), G, Bm, LLT, dtype)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.randn((hi - lo, ell), generator=gen, dtype=dtype, device=dev)
+    R.requires_grad_(True); Oprev.requires_grad_(True); x.requires_grad_(True)
+
+    def step():
+        R.grad = Oprev.grad = x.grad = None
+        mh, ld = D.chunked_mahal_and_det(R, Oprev, x, plan, rank)
+        ll = -0.5 * (mh + ld)
+        ll.backward()
+        return ll
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) + 2):          # two extra: the caching allocator needs them to settle at this size
+        step()
+    trace = LaunchTrace()
+    _native.TRACE = trace
+    clocks = ClockSampler(local)
+    sync()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ll = step().detach()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    trace.enabled = True
+    for _ in range(min(args.steps, 2)):
+        step()
+    sync()
+    trace.enabled = False
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    agg = trace.summary()
+    table = []
+    for (kind, m, batch), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        avg_ms = tot / cnt
+        algo = bytes_per_row_level(ell, s) * m * batch
+        table.append({"kernel": f"cr_level_{kind}_kernel<{args.dtype},{ell}>", "m": m, "batch": batch, "launches": cnt, "avg_ms": avg_ms,
+                      "algo_bytes": algo, "achieved_gbs": algo / (avg_ms * 1e-3) / 1e9, "frac": algo / (avg_ms * 1e-3) / 1e9 / peak})
+    top = table[0]
+    whole = bytes_per_row_total(ell, s) * (hi - lo)
+    roofline = {"bound": "hbm", "kernel": top["kernel"] + f" @ m={top['m']} x batch {top['batch']}", "achieved": top["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                "whole_step_rank0": {"algo_bytes": whole, "achieved": whole / (ms / args.steps * 1e-3) / 1e9,
+                                     "frac": whole / (ms / args.steps * 1e-3) / 1e9 / peak}}
+    if args.levels_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.levels_out)), exist_ok=True)
+        with open(args.levels_out, "w") as fh:
+            json.dump(table, fh, indent=1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        ncpu = min(n, 1_000_000)
+        v, dt = cpu_reference_rows_per_s(ncpu, ell, dtype, 3, warm=1)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"3 passes over a series of n={ncpu} (of {n}; host RAM bounds the reference at ~628 B/row), l={ell}, {args.dtype}, {dt:.1f} s"}
+    line = {"metric": METRIC, "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
+            "config": {"workload": f"configs[3]: single long series n={n}, l={ell}, {args.dtype}, chunk-partitioned CR + one all-gather",
+                       "n": n, "ell": ell, "sub_chunk_rows": plan.sub, "sub_chunks": plan.nsub, "parallelism": f"row-chunks x{world}",
+                       "l2": "inputs per step exceed L2; no explicit flush"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "gpu_launches": len(trace.records) // max(min(args.steps, 2), 1) * args.steps,
+            "clocks": clk, "loglik": float(ll)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,9 +307,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--levels-out", default=None, help="write the per-level launch table (JSON) here")
+    ap.add_argument("--workload", default="batch", choices=["batch", "long"],
+                    help="batch = configs[1] (default, the headline metric); long = configs[3], one series of --n rows")
+    ap.add_argument("--sub", type=int, default=None, help="long workload: rows per sub-chunk (power of two)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "long":
+        if args.n == WORKLOAD["n"]:
+            args.n, args.ell = 100_000_000, 4
+        return run_long(args)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -359,10 +471,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        series = 24 if (n * ell * ell) <= 10_000 * 64 else 4
-        v, dt = cpu_reference_rows_per_s(n, ell, dtype, series)
+        _, t_probe = cpu_reference_rows_per_s(n, ell, dtype, 4)            # calibrate: aim at ~12 s of CPU work
+        series = int(max(8, min(B, 12.0 / max(t_probe / 4, 1e-4))))
+        v, dt = cpu_reference_rows_per_s(n, ell, dtype, series, warm=0)
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{series} of {B} series (n={n}, l={ell}, {args.dtype}), oracle port of the reference + torch autograd, {dt:.1f} s"}
+               "sample": f"{series} of {B} series (n={n}, l={ell}, {args.dtype}), one series at a time (the reference has no batch axis), "
+                         f"oracle port of the reference + torch autograd, {dt:.1f} s"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -53,6 +53,7 @@ class FactorPack:
         self.G: List[torch.Tensor] = []
         self.X: List[Optional[torch.Tensor]] = []
         self.G_halo: List[torch.Tensor] = []
+        self.D_flat = self.F_flat = self.G_flat = self.X_flat = self.G_halo_flat = None   # packed storage behind the lists
         self.logdet: Optional[torch.Tensor] = None     # (B,) float64: 2 * sum log diag
         self.mahal: Optional[torch.Tensor] = None      # (B,) float64
         self.info: Optional[torch.Tensor] = None
@@ -106,9 +107,12 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
                   halo_O: Optional[torch.Tensor] = None) -> FactorPack:
     """Run CR levels 0..nlevels-1 (default: all, down to the last 1x1 system).
 
-    R (B,n,l,l), O (B,n-1,l,l) [any strided batch axis, rows contiguous], y (B,n,l) or None."""
+    R (B,n,l,l), O (B,n-1,l,l) [any strided batch axis, rows contiguous], y (B,n,l) or None.
+    The level loop runs inside libcrb200 (crb200_sweep_fwd); when bench.py's launch tracer is
+    active the per-level entries are used instead so that every launch can be timed."""
     B, n, ell = R.shape[0], R.shape[1], R.shape[2]
     dtype, dev = R.dtype, R.device
+    bs = ell * ell
     R, O, y = _rows_contiguous(R), _rows_contiguous(O), _rows_contiguous(y)
     ms_all = level_sizes(n)
     L = len(ms_all) if nlevels is None else min(nlevels, len(ms_all))
@@ -118,55 +122,84 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
     os_ = [counts(m)[1] for m in ms]
     gs = [counts(m)[2] for m in ms]
     if keep_factors:
-        _, pack.D = _alloc_levels(Es, (ell, ell), B, dtype, dev)
-        _, pack.F = _alloc_levels(os_, (ell, ell), B, dtype, dev)
-        _, pack.G = _alloc_levels(gs, (ell, ell), B, dtype, dev)
+        pack.D_flat, pack.D = _alloc_levels(Es, (ell, ell), B, dtype, dev)
+        pack.F_flat, pack.F = _alloc_levels(os_, (ell, ell), B, dtype, dev)
+        pack.G_flat, pack.G = _alloc_levels(gs, (ell, ell), B, dtype, dev)
     else:
+        pack.D_flat = pack.F_flat = pack.G_flat = None
         pack.D = [None] * L
         pack.F = [None] * L
         pack.G = [None] * L
     if y is not None and keep_factors:
-        _, pack.X = _alloc_levels(Es, (ell,), B, dtype, dev)
+        pack.X_flat, pack.X = _alloc_levels(Es, (ell,), B, dtype, dev)
     else:
+        pack.X_flat = None
         pack.X = [None] * L
     pack.logdet = torch.zeros(B, dtype=torch.float64, device=dev) if want_logdet else None
     pack.mahal = torch.zeros(B, dtype=torch.float64, device=dev) if y is not None else None
     pack.info = torch.zeros(L, dtype=torch.int32, device=dev)
     halo = halo_O is not None
+    Rh = yh = None
+    pack.G_halo_flat = None
     if halo:
         Rh = torch.zeros((B, ell, ell), dtype=dtype, device=dev)
         yh = torch.zeros((B, ell), dtype=dtype, device=dev)
         if keep_factors:
-            pack.G_halo = list(torch.empty((L, B, ell, ell), dtype=dtype, device=dev).unbind(0))
-        cur_halo = halo_O.contiguous()
-
-    cur_R, cur_O, cur_y = R, O, y
+            pack.G_halo_flat = torch.empty((L, B, ell, ell), dtype=dtype, device=dev)
+            pack.G_halo = list(pack.G_halo_flat.unbind(0))
+        halo_O = halo_O.contiguous()
+    # ping-pong scratch for the reduced systems: slot 0 <- levels 0,2,.. ; slot 1 <- levels 1,3,..
+    r0, r1 = n // 2, n // 4
+    scrR = (torch.empty((B * r0, ell, ell), dtype=dtype, device=dev) if r0 else None,
+            torch.empty((B * r1, ell, ell), dtype=dtype, device=dev) if r1 else None)
+    scrO = (torch.empty((B * r0, ell, ell), dtype=dtype, device=dev) if r0 > 1 else None,
+            torch.empty((B * r1, ell, ell), dtype=dtype, device=dev) if r1 > 1 else None)
+    scry = (torch.empty((B * r0, ell), dtype=dtype, device=dev) if (r0 and y is not None) else None,
+            torch.empty((B * r1, ell), dtype=dtype, device=dev) if (r1 and y is not None) else None)
+    On_h = (torch.empty((B, ell, ell), dtype=dtype, device=dev), torch.empty((B, ell, ell), dtype=dtype, device=dev)) if halo else (None, None)
     sR, sO = R.stride(0), (O.stride(0) if O.shape[1] > 0 else 0)
     sy = y.stride(0) if y is not None else 0
-    for k, m in enumerate(ms):
-        E, o, g = counts(m)
-        Rn = torch.empty((B, o, ell, ell), dtype=dtype, device=dev) if o > 0 else None
-        On = torch.empty((B, max(o - 1, 0), ell, ell), dtype=dtype, device=dev) if o > 1 else None
-        yn = torch.empty((B, o, ell), dtype=dtype, device=dev) if (o > 0 and y is not None) else None
-        fields = dict(batch=B, m=m, R=cur_R, O=cur_O if m > 1 else None, y=cur_y,
-                      strideR=sR, strideO=sO, stridey=sy,
-                      D=pack.D[k], F=pack.F[k] if o > 0 else None, G=pack.G[k] if g > 0 else None, xk=pack.X[k],
-                      Rn=Rn, On=On, yn=yn, logdet=pack.logdet, mahal=pack.mahal, info=pack.info[k:k + 1])
-        if halo:
-            On_h = torch.empty((B, ell, ell), dtype=dtype, device=dev)
-            fields.update(O_halo=cur_halo, G_halo=pack.G_halo[k] if keep_factors else None, On_halo=On_h, Rh_acc=Rh, yh_acc=yh)
-        _native.level_fwd(dtype, ell, **fields)
-        if halo:
-            cur_halo = On_h
-        cur_R, cur_O, cur_y = Rn, On, yn
-        sR, sO, sy = o * ell * ell, max(o - 1, 0) * ell * ell, o * ell
+
+    if not _native.tracing():
+        _native.sweep_fwd(dtype, ell, batch=B, n=n, nlevels=L, R=R, O=O if n > 1 else None, y=y,
+                          strideR=sR, strideO=sO, stridey=sy,
+                          D=pack.D_flat, F=pack.F_flat if (keep_factors and pack.F_flat.numel()) else None,
+                          G=pack.G_flat if (keep_factors and pack.G_flat.numel()) else None, X=pack.X_flat,
+                          scrR=scrR, scrO=scrO, scry=scry, logdet=pack.logdet, mahal=pack.mahal, info=pack.info,
+                          O_halo=halo_O, G_halo=pack.G_halo_flat, On_halo=On_h, Rh_acc=Rh, yh_acc=yh)
+    else:
+        cur_R, cur_O, cur_y, cur_halo = R, O, y, halo_O
+        for k, m in enumerate(ms):
+            E, o, g = counts(m)
+            slot = k & 1
+            fields = dict(batch=B, m=m, R=cur_R, O=cur_O if m > 1 else None, y=cur_y,
+                          strideR=sR, strideO=sO, stridey=sy,
+                          D=pack.D[k], F=pack.F[k] if o > 0 else None, G=pack.G[k] if g > 0 else None, xk=pack.X[k],
+                          Rn=scrR[slot] if o > 0 else None, On=scrO[slot] if o > 1 else None,
+                          yn=scry[slot] if (o > 0 and y is not None) else None,
+                          logdet=pack.logdet, mahal=pack.mahal, info=pack.info[k:k + 1])
+            if halo:
+                fields.update(O_halo=cur_halo, G_halo=pack.G_halo[k] if keep_factors else None, On_halo=On_h[slot], Rh_acc=Rh, yh_acc=yh)
+                cur_halo = On_h[slot]
+            _native.level_fwd(dtype, ell, **fields)
+            cur_R, cur_O, cur_y = fields["Rn"], fields["On"], fields["yn"]
+            sR, sO, sy = o * bs, max(o - 1, 0) * bs, o * ell
     if pack.logdet is not None:
         pack.logdet.mul_(2.0)    # log|J| = 2 sum log diag(K)   (reference det :458, mahal_and_det :438)
+    last = (L - 1) & 1
     if L < len(ms_all):
-        pack.rest = (cur_R, cur_O, cur_y)
+        o = ms[-1] // 2
+        pack.rest = (scrR[last][:B * o].view(B, o, ell, ell),
+                     scrO[last][:B * (o - 1)].view(B, o - 1, ell, ell) if o > 1 else None,
+                     scry[last][:B * o].view(B, o, ell) if y is not None else None)
     if halo:
-        pack.halo_out = dict(Rh=Rh, yh=yh, O=cur_halo)
+        pack.halo_out = dict(Rh=Rh, yh=yh, O=On_h[last])
     return pack
+
+
+def _flat_levels(levels: Sequence[torch.Tensor]):
+    """Pack per-level (B, rows_k, ...) tensors back to back (the layout crb200_sweep_bwd reads)."""
+    return torch.cat([t.reshape(-1) for t in levels]) if len(levels) else None
 
 
 def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Sequence[torch.Tensor]] = None,
@@ -177,45 +210,87 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
     grad  (gm, gd): (B,) float64 cotangents -> level 0 emits gR, gO, gx instead
     top   (Sd, So, w) of the system left by an early-stopped forward sweep
     halo  dict(Sd=(B,l,l), w=(B,l), So=(B,l,l)) values at / towards the virtual left node
-    out   optional (Sd, So, w) tensors to write level 0 into"""
+    out   optional (Sd, So, w) tensors to write level 0 into: (B,m,l,l), (B,m-1,l,l), (B,m,l), any batch
+          stride, rows contiguous"""
     B, ell, dtype = pack.batch, pack.ell, pack.dtype
     dev = pack.D[0].device
-    xs = list(xs) if xs is not None else pack.X
-    if w and any(x is None for x in xs):
-        raise ValueError("back-solve needs the per-level right-hand sides")
-    Sd_in = So_in = w_in = None
-    if top is not None:
-        Sd_in, So_in, w_in = top
-    use_halo = halo is not None
-    So_h = halo["So"] if use_halo and sigma else None
-    Sd = So = wv = None
-    for k in range(pack.nlevels - 1, -1, -1):
-        m = pack.ms[k]
-        E, o, g = counts(m)
-        last = k == 0
-        if last and out is not None:
-            Sd, So, wv = out
+    bs = ell * ell
+    L = pack.nlevels
+    n = pack.ms[0]
+    if w:
+        if xs is None:
+            if pack.X_flat is None:
+                raise ValueError("back-solve needs the per-level right-hand sides")
+            X_flat, X_levels = pack.X_flat, pack.X
         else:
-            Sd = torch.empty((B, m, ell, ell), dtype=dtype, device=dev) if sigma else None
-            So = torch.empty((B, max(m - 1, 0), ell, ell), dtype=dtype, device=dev) if sigma else None
-            wv = torch.empty((B, m, ell), dtype=dtype, device=dev) if w else None
-        fields = dict(batch=B, m=m, D=pack.D[k], F=pack.F[k] if o > 0 else None, G=pack.G[k] if g > 0 else None,
-                      xk=xs[k] if w else None, Sd_in=Sd_in, So_in=So_in if o > 1 else None, w_in=w_in,
-                      Sd_out=Sd, So_out=So if m > 1 else None, w_out=wv,
-                      strideSd=m * ell * ell, strideSo=max(m - 1, 0) * ell * ell, stridew=m * ell,
-                      gm=None, gd=None, grad_mode=0)
-        if last and grad is not None:
-            fields.update(gm=grad[0], gd=grad[1], grad_mode=1)
-        if use_halo:
-            So_h_out = torch.empty((B, ell, ell), dtype=dtype, device=dev) if sigma else None
-            fields.update(G_halo=pack.G_halo[k], Sd_halo=halo["Sd"] if sigma else None, w_halo=halo["w"] if w else None,
-                          So_halo_in=So_h if (sigma and o > 0) else None, So_halo_out=So_h_out)
-        _native.level_bwd(dtype, ell, **fields)
-        if use_halo and sigma:
-            So_h = So_h_out
-        Sd_in, So_in, w_in = Sd, So, wv
+            X_levels = [x.contiguous() for x in xs]
+            X_flat = _flat_levels(X_levels)
+    else:
+        X_flat, X_levels = None, [None] * L
+    D_flat = getattr(pack, "D_flat", None)
+    if D_flat is None:
+        pack.D_flat, pack.F_flat, pack.G_flat = _flat_levels(pack.D), _flat_levels(pack.F), _flat_levels(pack.G)
+    top_Sd = top_So = top_w = None
+    if top is not None:
+        top_Sd, top_So, top_w = (t.contiguous() if t is not None else None for t in top)
+    if out is not None:
+        Sd, So, wv = out
+    else:
+        Sd = torch.empty((B, n, ell, ell), dtype=dtype, device=dev) if sigma else None
+        So = torch.empty((B, max(n - 1, 0), ell, ell), dtype=dtype, device=dev) if sigma else None
+        wv = torch.empty((B, n, ell), dtype=dtype, device=dev) if w else None
+    m1 = pack.ms[1] if L > 1 else 0
+    m2 = pack.ms[2] if L > 2 else 0
+    mk = lambda rows, *tr: torch.empty((B * rows,) + tr, dtype=dtype, device=dev) if rows else None
+    scrSd = (mk(m2, ell, ell) if sigma else None, mk(m1, ell, ell) if sigma else None)
+    scrSo = (mk(m2, ell, ell) if sigma else None, mk(m1, ell, ell) if sigma else None)
+    scrw = (mk(m2, ell) if w else None, mk(m1, ell) if w else None)
+    use_halo = halo is not None
+    So_h = (torch.empty((B, ell, ell), dtype=dtype, device=dev), torch.empty((B, ell, ell), dtype=dtype, device=dev)) if (use_halo and sigma) else (None, None)
+    So_h_out = torch.empty((B, ell, ell), dtype=dtype, device=dev) if (use_halo and sigma) else None
+    gm, gd = (grad if grad is not None else (None, None))
+    stride0 = lambda t, default: (t.stride(0) if (t is not None and t.dim() > 1 and t.shape[0] > 1) else default)
+
+    if not _native.tracing():
+        _native.sweep_bwd(dtype, ell, batch=B, n=n, nlevels=L,
+                          D=pack.D_flat, F=pack.F_flat if (pack.F_flat is not None and pack.F_flat.numel()) else None,
+                          G=pack.G_flat if (pack.G_flat is not None and pack.G_flat.numel()) else None, X=X_flat,
+                          top_Sd=top_Sd if sigma else None, top_So=top_So if sigma else None, top_w=top_w if w else None,
+                          Sd_out=Sd, So_out=So if (So is not None and n > 1) else None, w_out=wv,
+                          strideSd=stride0(Sd, n * bs), strideSo=stride0(So, max(n - 1, 0) * bs), stridew=stride0(wv, n * ell),
+                          scrSd=scrSd, scrSo=scrSo, scrw=scrw, gm=gm, gd=gd, grad_mode=1 if grad is not None else 0,
+                          G_halo=pack.G_halo_flat if use_halo else None, Sd_halo=halo["Sd"].contiguous() if (use_halo and sigma) else None,
+                          w_halo=halo["w"].contiguous() if (use_halo and w) else None,
+                          So_halo_in=halo["So"].contiguous() if (use_halo and sigma) else None, So_halo=So_h, So_halo_out=So_h_out)
+    else:
+        Sd_in, So_in, w_in = top_Sd, top_So, top_w
+        so_h = halo["So"].contiguous() if (use_halo and sigma) else None
+        for k in range(L - 1, -1, -1):
+            m = pack.ms[k]
+            E, o, g = counts(m)
+            slot = k & 1
+            if k == 0:
+                oSd, oSo, ow = Sd, So, wv
+                sSd, sSo, sw = stride0(Sd, n * bs), stride0(So, max(n - 1, 0) * bs), stride0(wv, n * ell)
+            else:
+                oSd, oSo, ow = scrSd[slot], scrSo[slot], scrw[slot]
+                sSd, sSo, sw = m * bs, max(m - 1, 0) * bs, m * ell
+            fields = dict(batch=B, m=m, D=pack.D[k], F=pack.F[k] if o > 0 else None, G=pack.G[k] if g > 0 else None,
+                          xk=X_levels[k] if w else None, Sd_in=Sd_in if sigma else None, So_in=So_in if (sigma and o > 1) else None,
+                          w_in=w_in if w else None, Sd_out=oSd, So_out=oSo if m > 1 else None, w_out=ow,
+                          strideSd=sSd, strideSo=sSo, stridew=sw, gm=None, gd=None, grad_mode=0)
+            if k == 0 and grad is not None:
+                fields.update(gm=gm, gd=gd, grad_mode=1)
+            if use_halo:
+                h_out = (So_h_out if k == 0 else So_h[slot]) if sigma else None
+                fields.update(G_halo=pack.G_halo[k], Sd_halo=halo["Sd"].contiguous() if sigma else None,
+                              w_halo=halo["w"].contiguous() if w else None,
+                              So_halo_in=so_h if (sigma and o > 0) else None, So_halo_out=h_out)
+                so_h = h_out
+            _native.level_bwd(dtype, ell, **fields)
+            Sd_in, So_in, w_in = oSd, oSo, ow
     if use_halo:
-        return Sd, So, wv, So_h
+        return Sd, So, wv, So_h_out
     return Sd, So, wv
 
 

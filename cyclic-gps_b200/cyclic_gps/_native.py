@@ -48,8 +48,33 @@ class HsArgs(C.Structure):
                 ("xk", _vp), ("yn", _vp), ("mahal", _vp)]
 
 
+class SweepFwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("n", _i), ("nlevels", _i),
+                ("R", _vp), ("O", _vp), ("y", _vp),
+                ("strideR", _ll), ("strideO", _ll), ("stridey", _ll),
+                ("D", _vp), ("F", _vp), ("G", _vp), ("X", _vp),
+                ("scrR", _vp * 2), ("scrO", _vp * 2), ("scry", _vp * 2),
+                ("logdet", _vp), ("mahal", _vp), ("info", _vp),
+                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp * 2), ("Rh_acc", _vp), ("yh_acc", _vp),
+                ("variant", _i)]
+
+
+class SweepBwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("n", _i), ("nlevels", _i),
+                ("D", _vp), ("F", _vp), ("G", _vp), ("X", _vp),
+                ("top_Sd", _vp), ("top_So", _vp), ("top_w", _vp),
+                ("Sd_out", _vp), ("So_out", _vp), ("w_out", _vp),
+                ("strideSd", _ll), ("strideSo", _ll), ("stridew", _ll),
+                ("scrSd", _vp * 2), ("scrSo", _vp * 2), ("scrw", _vp * 2),
+                ("gm", _vp), ("gd", _vp), ("grad_mode", _i),
+                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp),
+                ("So_halo", _vp * 2), ("So_halo_out", _vp),
+                ("variant", _i)]
+
+
 EXPORTS = ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
-           "crb200_level_bwd", "crb200_level_halfsolve", "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes")
+           "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd",
+           "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes")
 
 _lib = None
 _lock = threading.Lock()
@@ -81,6 +106,10 @@ def load():
         lib.crb200_level_bwd.argtypes = [_i, _i, C.POINTER(BwdArgs), _vp]
         lib.crb200_level_halfsolve.restype = _i
         lib.crb200_level_halfsolve.argtypes = [_i, _i, C.POINTER(HsArgs), _vp]
+        lib.crb200_sweep_fwd.restype = _i
+        lib.crb200_sweep_fwd.argtypes = [_i, _i, C.POINTER(SweepFwdArgs), _vp]
+        lib.crb200_sweep_bwd.restype = _i
+        lib.crb200_sweep_bwd.argtypes = [_i, _i, C.POINTER(SweepBwdArgs), _vp]
         for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
             getattr(lib, name).restype = _i
             getattr(lib, name).argtypes = [_i, _i]
@@ -123,6 +152,10 @@ def _fill(struct, fields):
     for k, v in fields.items():
         if isinstance(v, torch.Tensor) or v is None:
             setattr(struct, k, _ptr(v))
+        elif isinstance(v, (tuple, list)):          # pair of ping-pong buffers
+            arr = getattr(struct, k)
+            for i, t in enumerate(v):
+                arr[i] = _ptr(t)
         else:
             setattr(struct, k, v)
     return struct
@@ -157,6 +190,28 @@ def level_bwd(dtype: torch.dtype, ell: int, **fields):
 
 def level_halfsolve(dtype: torch.dtype, ell: int, **fields):
     _traced("halfsolve", load().crb200_level_halfsolve, dtype, ell, _fill(HsArgs(), fields))
+
+
+def sweep_fwd(dtype: torch.dtype, ell: int, **fields):
+    """All forward levels in one library call (the level loop runs in C)."""
+    fields.setdefault("variant", VARIANT)
+    a = _fill(SweepFwdArgs(), fields)
+    tr = TRACE
+    if tr is not None and getattr(tr, "enabled", True):
+        # per-launch tracing needs one host call per level: bench.py switches to the level entries
+        raise RuntimeError("launch tracing is only available through the per-level entries")
+    _check(load().crb200_sweep_fwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_fwd")
+
+
+def sweep_bwd(dtype: torch.dtype, ell: int, **fields):
+    fields.setdefault("variant", VARIANT)
+    a = _fill(SweepBwdArgs(), fields)
+    _check(load().crb200_sweep_bwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_bwd")
+
+
+def tracing() -> bool:
+    tr = TRACE
+    return tr is not None and getattr(tr, "enabled", True)
 
 
 def tile_nodes(dtype: torch.dtype, ell: int):

@@ -347,9 +347,12 @@ class _MahalAndDetFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_mahal, g_det):
         pack = ctx.pack
+        if pack is None:
+            raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
         dev = pack.D[0].device
         as_vec = lambda g: g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
         gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(as_vec(g_mahal), as_vec(g_det)))
+        ctx.pack = None                                # free the packed factors (~3 n l^2 elements) right away
         b = ctx.batched
         return (_to_caller(gR, b, ctx.devs[0]), _to_caller(gO, b, ctx.devs[1]), _to_caller(gx, b, ctx.devs[2]), None)
 

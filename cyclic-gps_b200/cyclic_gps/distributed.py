@@ -196,8 +196,9 @@ def chunked_backward(ctx, g_mahal: float, g_logdet: float):
     ell = rshape[-1]
     sub = plan.sub
     n_loc = rshape[0]
+    bs = ell * ell
     gR = torch.empty(rshape, dtype=dtype, device=dev)
-    gO = torch.zeros(rshape, dtype=dtype, device=dev)
+    gO = torch.empty(rshape, dtype=dtype, device=dev)
     gx = torch.empty((n_loc, ell), dtype=dtype, device=dev)
     # boundary solution: Sigma and w at every boundary node (no gradient scaling here)
     if ctx.bpack is not None:
@@ -227,20 +228,19 @@ def chunked_backward(ctx, g_mahal: float, g_logdet: float):
         So_h = torch.where(ok.view(-1, 1, 1), Sbo[idc.clamp(max=max(Sbo.shape[0] - 1, 0))] if Sbo.shape[0] > 0 else zero_b.expand(S, -1, -1), zero_b)
         top = (Sbd[gidx].unsqueeze(1).contiguous(), None, wb[gidx].unsqueeze(1).contiguous())
         halo = dict(Sd=Sd_h, w=w_h, So=So_h.contiguous())
-        Sd, So, wv, So_left = engine.backward_sweep(ctx.pack, sigma=True, w=True, grad=cot(S), top=top, halo=halo)
-        gR[:S * sub] = Sd.reshape(S * sub, ell, ell)
-        gx[:S * sub] = wv.reshape(S * sub, ell)
-        gOv = gO[:S * sub].view(S, sub, ell, ell)
-        gOv[:, 1:] = So
-        gOv[:, 0] = So_left
+        # level 0 writes straight into the gradient tensors (rows of a sub-chunk are contiguous; the
+        # off-diagonal gradient skips the first block of every sub-chunk, which is the halo coupling)
+        out = (gR[:S * sub].view(S, sub, ell, ell),
+               torch.as_strided(gO, (S, sub - 1, ell, ell), (sub * bs, bs, ell, 1), gO.storage_offset() + bs),
+               gx[:S * sub].view(S, sub, ell))
+        _, _, _, So_left = engine.backward_sweep(ctx.pack, sigma=True, w=True, grad=cot(S), top=top, halo=halo, out=out)
+        gO[0:S * sub:sub] = So_left
     if tail > 0:
         t0 = S * sub
         Sd_h, w_h, idc, ok = halo_for(g0 + S, 1)
         halo = dict(Sd=Sd_h, w=w_h, So=zero_b.clone())
-        Sd, So, wv, So_left = engine.backward_sweep(ctx.pack_tail, sigma=True, w=True, grad=cot(1), halo=halo)
-        gR[t0:] = Sd[0]
-        gx[t0:] = wv[0]
-        gO[t0 + 1:] = So[0]
+        out = (gR[t0:].unsqueeze(0), gO[t0 + 1:].unsqueeze(0), gx[t0:].unsqueeze(0))
+        _, _, _, So_left = engine.backward_sweep(ctx.pack_tail, sigma=True, w=True, grad=cot(1), halo=halo, out=out)
         gO[t0] = So_left[0]
     if plan.rows(rank)[0] == 0 and n_loc > 0:
         gO[0].zero_()                                               # row 0 has no predecessor
@@ -261,7 +261,10 @@ class ChunkedMahalAndDet(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_mahal, g_det):
+        if ctx.c is None:
+            raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
         gR, gO, gx = chunked_backward(ctx.c, float(g_mahal), float(g_det))
+        ctx.c = None                                   # release ~3 n l^2 elements of factors now, not at graph teardown
         return gR, gO, gx, None, None, None, None
 
 

@@ -86,6 +86,45 @@ typedef struct crb200_hs_args {
   double* mahal;
 } crb200_hs_args;
 
+/* Whole sweeps: the level loop runs inside the library (one host call, ~3 us per level instead of a
+ * Python round trip).  Packed per-level storage: level k of a family starts at element offset
+ * batch * unit * sum_{j<k} rows_j  with rows_j = E_j (D, X), o_j (F), g_j (G) and unit = l*l (l for X);
+ * m_0 = n, m_{k+1} = floor(m_k / 2).  Ping-pong scratch: level k writes its result to slot [k & 1].
+ *
+ * Forward = decompose (:288-309) / mahal_and_det (:380-438) / the halo sweep of a sub-chunk batch.
+ * After the call the system left below level nlevels-1 (if any) sits in scr*[(nlevels-1)&1] and the last
+ * halo coupling in On_halo[(nlevels-1)&1]. */
+typedef struct crb200_sweep_fwd_args {
+  int batch, n, nlevels;
+  const void* R; const void* O; const void* y;
+  long long strideR, strideO, stridey;
+  void* D; void* F; void* G; void* X;                 /* packed factors; D/F/G NULL => not kept; X NULL => x_k not kept */
+  void* scrR[2]; void* scrO[2]; void* scry[2];        /* [0] >= batch*floor(n/2) rows, [1] >= batch*floor(n/4) rows */
+  double* logdet; double* mahal; int* info;           /* info: nlevels ints, zero-initialised by the caller */
+  const void* O_halo; void* G_halo;                   /* G_halo: nlevels * batch blocks (NULL => not kept) */
+  void* On_halo[2]; void* Rh_acc; void* yh_acc;
+  int variant;
+} crb200_sweep_fwd_args;
+
+/* Backward = backhalfsolve (:341-377) + inverse_blocks (:470-503) + gradient assembly, deepest level first.
+ * Level k >= 1 writes slot [k & 1] (slot [1] >= batch*m_1 rows, slot [0] >= batch*m_2 rows); level 0 writes
+ * Sd_out / So_out / w_out.  The final halo off-diagonal block goes to So_halo_out. */
+typedef struct crb200_sweep_bwd_args {
+  int batch, n, nlevels;
+  const void* D; const void* F; const void* G; const void* X;
+  const void* top_Sd; const void* top_So; const void* top_w;   /* solution of the system below the deepest level (or NULL) */
+  void* Sd_out; void* So_out; void* w_out;
+  long long strideSd, strideSo, stridew;
+  void* scrSd[2]; void* scrSo[2]; void* scrw[2];
+  const double* gm; const double* gd; int grad_mode;
+  const void* G_halo; const void* Sd_halo; const void* w_halo; const void* So_halo_in;
+  void* So_halo[2]; void* So_halo_out;
+  int variant;
+} crb200_sweep_bwd_args;
+
+int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* args, void* stream);
+int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* args, void* stream);
+
 int crb200_version(void);
 int crb200_max_ell(void);
 /* cudaError_t of the last failing launch on the calling thread's most recent call (0 if none). */

@@ -145,6 +145,11 @@ def backward_sweep(pack, *, sigma, w, xs=None, grad=None, top=None, halo=None, o
         if halo is not None:
             Soh_all.append(Soh)
     res = (torch.stack(Sd_all), torch.stack(So_all), torch.stack(w_all))
+    if out is not None:
+        for dst, src in zip(out, res):
+            if dst is not None and dst.numel():
+                dst.copy_(src)
+        res = tuple(out)
     if halo is not None:
         return res + (torch.stack(Soh_all),)
     return res
