@@ -23,6 +23,9 @@ for p in (os.path.join(ROOT, "cyclic-gps_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
+
 import torch  # noqa: E402
 
 WORKLOAD = dict(batch=1024, n=10_000, ell=8, dtype="float32")
@@ -39,6 +42,11 @@ def bytes_per_row_level(ell, s):
 
 def bytes_per_row_total(ell, s):
     return (18 * ell * ell + 8 * ell) * s    # fwd + bwd over all levels, per original block-row
+
+
+def kernel_family(ell, s):
+    """Which kernel family libcrb200 dispatches to."""
+    return "tpn" if s * ell * ell <= 256 else "level"
 
 
 def peaks():
@@ -263,7 +271,7 @@ def run_long(args):
     for (kind, m, batch), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         avg_ms = tot / cnt
         algo = bytes_per_row_level(ell, s) * m * batch
-        table.append({"kernel": f"cr_level_{kind}_kernel<{args.dtype},{ell}>", "m": m, "batch": batch, "launches": cnt, "avg_ms": avg_ms,
+        table.append({"kernel": f"cr_{kernel_family(ell, s)}_{kind}_kernel<{args.dtype},{ell}>", "m": m, "batch": batch, "launches": cnt, "avg_ms": avg_ms,
                       "algo_bytes": algo, "achieved_gbs": algo / (avg_ms * 1e-3) / 1e9, "frac": algo / (avg_ms * 1e-3) / 1e9 / peak})
     top = table[0]
     whole = bytes_per_row_total(ell, s) * (hi - lo)
@@ -347,10 +355,11 @@ def main():
         Rr.grad = Or.grad = xr.grad = None
         mm, dd = cr.mahal_and_det(Rr, Or, xr)
         ll = -0.5 * (mm.double().sum() + dd.double().sum())
-        if dist is not None:
-            dist.all_reduce(ll)
         ll.backward()
-        return ll
+        tot = ll.detach().clone()
+        if dist is not None:
+            dist.all_reduce(tot)          # the job-wide log-likelihood (the only collective of this workload)
+        return tot
 
     def sync():
         torch.cuda.synchronize()
@@ -398,19 +407,39 @@ def main():
         hout = torch.empty((2, B), dtype=dtype, pin_memory=True)
         dR, dO, dx = torch.empty_like(R), torch.empty_like(O), torch.empty_like(x)
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        nchunk = 8 if B % 8 == 0 and B >= 64 else 1
+        bsz = B // nchunk
+
         def e2e_step():
-            dR.requires_grad_(False); dO.requires_grad_(False); dx.requires_grad_(False)
-            dR.copy_(hR, non_blocking=True); dO.copy_(hO, non_blocking=True); dx.copy_(hx, non_blocking=True)
-            dR.requires_grad_(True); dO.requires_grad_(True); dx.requires_grad_(True)
-            dR.grad = dO.grad = dx.grad = None
-            mm, dd = cr.mahal_and_det(dR, dO, dx)
-            ll = -0.5 * (mm.double().sum() + dd.double().sum())
+            """Host buffers in, per-series scalars out, through the public API (cr.mahal_and_det + backward).
+            The batch is cut into chunks of series; chunk c+1 crosses PCIe on a copy stream while chunk c computes."""
+            main = torch.cuda.current_stream()
+            copy_stream.wait_stream(main)                 # previous step is done with the device buffers
+            ready = []
+            with torch.cuda.stream(copy_stream):
+                for c in range(nchunk):
+                    sl = slice(c * bsz, (c + 1) * bsz)
+                    dR[sl].copy_(hR[sl], non_blocking=True)
+                    dO[sl].copy_(hO[sl], non_blocking=True)
+                    dx[sl].copy_(hx[sl], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    ready.append(ev)
+            tot = torch.zeros((), dtype=torch.float64, device=dev)
+            for c in range(nchunk):
+                sl = slice(c * bsz, (c + 1) * bsz)
+                main.wait_event(ready[c])
+                Rc, Oc, xc = (t[sl].detach().requires_grad_(True) for t in (dR, dO, dx))
+                mm, dd = cr.mahal_and_det(Rc, Oc, xc)
+                ll = -0.5 * (mm.double().sum() + dd.double().sum())
+                ll.backward()
+                tot += ll.detach()
+                hout[0, sl].copy_(mm.detach(), non_blocking=True)
+                hout[1, sl].copy_(dd.detach(), non_blocking=True)
             if dist is not None:
-                dist.all_reduce(ll)
-            ll.backward()
-            hout[0].copy_(mm.detach(), non_blocking=True)
-            hout[1].copy_(dd.detach(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()     # the caller holds the result on the host
+                dist.all_reduce(tot)
+            main.synchronize()                            # the caller holds the result on the host
             return hout
 
         e2e_step()
@@ -430,7 +459,8 @@ def main():
             ms2 = float(t)
         h2d = (hR.numel() + hO.numel() + hx.numel()) * s
         e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
-               "ms_per_step": ms2, "steps": k2}
+               "ms_per_step": ms2, "steps": k2, "pipeline": f"{nchunk} chunks of {bsz} series, H2D on a copy stream overlapped with compute",
+               "h2d_gbs": h2d / (ms2 * 1e-3) / 1e9}
         del hR, hO, hx, dR, dO, dx
 
     if rank != 0:
@@ -442,10 +472,11 @@ def main():
     peak, peak_src = peaks()
     agg = trace.summary()
     table = []
+    fam = kernel_family(ell, s)
     for (kind, m, batch), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         avg_ms = tot / cnt
         algo = bytes_per_row_level(ell, s) * m * batch
-        table.append({"kernel": f"cr_level_{kind}_kernel<{args.dtype},{ell}>", "m": m, "batch": batch, "launches": cnt,
+        table.append({"kernel": f"cr_{fam}_{kind}_kernel<{args.dtype},{ell}>", "kind": kind, "m": m, "batch": batch, "launches": cnt,
                       "avg_ms": avg_ms, "algo_bytes": algo, "achieved_gbs": algo / (avg_ms * 1e-3) / 1e9,
                       "frac": algo / (avg_ms * 1e-3) / 1e9 / peak})
     top = table[0]
@@ -457,11 +488,15 @@ def main():
                 "whole_step": {"algo_bytes": bytes_per_row_total(ell, s) * B * n,
                                "achieved": bytes_per_row_total(ell, s) * B * n / (ms / args.steps * 1e-3) / 1e9,
                                "frac": bytes_per_row_total(ell, s) * B * n / (ms / args.steps * 1e-3) / 1e9 / peak}}
+    # DRAM bytes of that kernel from the committed ncu --set full capture, scaled to this launch's rows
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
-                roofline["traffic"] = json.load(fh).get(top["kernel"].split("<")[0] + f"@{args.dtype},{ell}")
+                ent = json.load(fh).get(top["kernel"].split("<")[0] + f"@{args.dtype},{ell}")
+            if ent:
+                roofline["traffic"] = ent["bytes_per_row"] * top["m"] * top["batch"]
+                roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read+write per block-row of the level-0 launch, x rows of this launch)"
         except Exception:
             pass
     if args.levels_out:

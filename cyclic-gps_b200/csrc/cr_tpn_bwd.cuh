@@ -34,80 +34,6 @@ struct TpnBwdCfg {
 };
 
 
-// rows [R0,R1) of Sigma_{2e,2e-1} = -(Q^T S~_d[e-1]^T + P^T S~_o[e-1]), written to `dstC`
-template <typename T, int L, int R0, int R1>
-__device__ __forceinline__ void tpn_bwd_so_rows(const T (&P)[L][L], const T (&Q)[L][L], const T* sdL, const T* so_in, T* dstC, bool has_so) {
-  if constexpr (R1 > R0) {
-    T acc[R1 - R0][L];
-#pragma unroll
-    for (int c = 0; c < L; ++c) {
-      T a0[L];
-      lds_row<T, L>(a0, sdL + c * L);
-#pragma unroll
-      for (int r = R0; r < R1; ++r) {
-        T s = T(0);
-#pragma unroll
-        for (int k = 0; k < L; ++k) s = fma(-Q[k][r], a0[k], s);
-        acc[r - R0][c] = s;
-      }
-    }
-    if (has_so) {
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        T so[L];
-        lds_row<T, L>(so, so_in + k * L);
-#pragma unroll
-        for (int r = R0; r < R1; ++r)
-#pragma unroll
-          for (int c = 0; c < L; ++c) acc[r - R0][c] = fma(-P[k][r], so[c], acc[r - R0][c]);
-      }
-    }
-#pragma unroll
-    for (int r = R0; r < R1; ++r) sts_row<T, L>(dstC + r * L, acc[r - R0]);
-  }
-}
-
-// rows [R0,R1) of Sigma_{2e,2e} = Di^T Di - S_d^T P - (S_o^T) Q, in place in `A` (which holds Di^T Di)
-template <typename T, int L, int R0, int R1>
-__device__ __forceinline__ void tpn_bwd_se_rows(const T (&P)[L][L], const T (&Q)[L][L], T* A, const T* sdB, const T* stC, bool has_odd,
-                                                bool has_left, bool grad, T gd, T gm, const T (&wv)[L]) {
-  if constexpr (R1 > R0) {
-    T acc[R1 - R0][L];
-#pragma unroll
-    for (int r = R0; r < R1; ++r) lds_row<T, L>(acc[r - R0], A + r * L);
-    if (has_odd) {
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        T sd[L];
-        lds_row<T, L>(sd, sdB + k * L);
-#pragma unroll
-        for (int r = R0; r < R1; ++r)
-#pragma unroll
-          for (int c = 0; c < L; ++c) acc[r - R0][c] = fma(-sd[r], P[k][c], acc[r - R0][c]);
-      }
-    }
-    if (has_left) {
-#pragma unroll
-      for (int r = R0; r < R1; ++r) {
-        T st[L];
-        lds_row<T, L>(st, stC + r * L);
-#pragma unroll
-        for (int k = 0; k < L; ++k)
-#pragma unroll
-          for (int c = 0; c < L; ++c) acc[r - R0][c] = fma(-st[k], Q[k][c], acc[r - R0][c]);
-      }
-    }
-#pragma unroll
-    for (int r = R0; r < R1; ++r) {
-      if (grad) {
-#pragma unroll
-        for (int c = 0; c < L; ++c) acc[r - R0][c] = gd * acc[r - R0][c] - gm * wv[r] * wv[c];
-      }
-      sts_row<T, L>(A + r * L, acc[r - R0]);
-    }
-  }
-}
-
 template <typename T, int L>
 __global__ void __launch_bounds__(32, TpnBwdCfg<T, L>::MIN_CTAS)
 cr_tpn_bwd_kernel(const LevelBwdArgs a) {
@@ -287,11 +213,11 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         lds_row<T, L>(sig, N + Cf::SD + r * L);
         lds_row<T, L>(so, N + Cf::SO + r * L);
 #pragma unroll
-        for (int c = 0; c < L; ++c) {
-          T s = T(0);
+        for (int c = 0; c < L; ++c) out[c] = T(0);
 #pragma unroll
-          for (int k = 0; k < L; ++k) { s = fma(-sig[k], P[k][c], s); s = fma(has_so ? -so[k] : T(0), Q[k][c], s); }
-          out[c] = s;
+        for (int k = 0; k < L; ++k) {
+          axpy_row<T, L>(out, -sig[k], P[k]);
+          axpy_row<T, L>(out, has_so ? -so[k] : T(0), Q[k]);
         }
         sts_row<T, L>(N + Cf::B + r * L, out);
       }
@@ -306,11 +232,11 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < L; ++k) socol[k] = has_so ? N[Cf::SO + k * L + c] : T(0);
 #pragma unroll
-        for (int r = 0; r < L; ++r) {
-          T s = T(0);
+        for (int r = 0; r < L; ++r) st[r] = T(0);
 #pragma unroll
-          for (int k = 0; k < L; ++k) { s = fma(-Q[k][r], a0[k], s); s = fma(-P[k][r], socol[k], s); }
-          st[r] = s;
+        for (int k = 0; k < L; ++k) {
+          axpy_row<T, L>(st, -a0[k], Q[k]);
+          axpy_row<T, L>(st, -socol[k], P[k]);
         }
 #pragma unroll
         for (int r = 0; r < L; ++r) N[Cf::C + r * L + c] = st[r];
@@ -331,11 +257,9 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < L; ++k) sdcol[k] = has_odd ? N[Cf::B + k * L + r] : T(0);
 #pragma unroll
-        for (int c = 0; c < L; ++c) {
-          T s = acc[c];
-#pragma unroll
-          for (int k = 0; k < L; ++k) { s = fma(-sdcol[k], P[k][c], s); s = fma(has_left ? -st[k] : T(0), Q[k][c], s); }
-          acc[c] = s;
+        for (int k = 0; k < L; ++k) {
+          axpy_row<T, L>(acc, -sdcol[k], P[k]);
+          axpy_row<T, L>(acc, has_left ? -st[k] : T(0), Q[k]);
         }
         if (grad) {
           T wr = T(0);

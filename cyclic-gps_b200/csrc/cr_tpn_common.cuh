@@ -84,6 +84,28 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
 // point (keeps the register live set of the fully unrolled row loops bounded)
 __device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
 
+// acc[c] += s * row[c] for a register-resident row.  A packed FFMA2 (fma.rn.f32x2, new on sm_100)
+// variant was measured on B200 and is NOT used: it issues at half the rate of FFMA, the aligned register
+// pairs cost spills, and the l=8 backward level got 3 % slower (profiles/r1_summary.md).
+#ifndef CRB200_USE_FFMA2
+#define CRB200_USE_FFMA2 0
+#endif
+template <typename T, int L>
+__device__ __forceinline__ void axpy_row(T (&acc)[L], T s, const T (&row)[L]) {
+  if constexpr (CRB200_USE_FFMA2 && sizeof(T) == 4 && (L % 2) == 0) {
+    const float2 ss = make_float2(s, s);
+#pragma unroll
+    for (int c = 0; c < L; c += 2) {
+      const float2 r = __ffma2_rn(ss, make_float2(row[c], row[c + 1]), make_float2(acc[c], acc[c + 1]));
+      acc[c] = r.x;
+      acc[c + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < L; ++c) acc[c] = fma(s, row[c], acc[c]);
+  }
+}
+
 // record stride (elements): payload rounded up to an ODD number of 16-byte chunks, so that the
 // 8 lanes of a quarter warp hit 8 different 16-byte bank groups on per-thread vector accesses
 template <typename T>
