@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--workload", default="batch", choices=["batch", "long"],
                     help="batch = configs[1] (default, the headline metric); long = configs[3], one series of --n rows")
     ap.add_argument("--sub", type=int, default=None, help="long workload: rows per sub-chunk (power of two)")
+    ap.add_argument("--variant", type=int, default=0, help="force a kernel family (0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -344,6 +345,7 @@ def main():
 
     from cyclic_gps import _native, cyclic_reduction as cr
     _native.load()
+    _native.VARIANT = args.variant
     B, n, ell = args.batch, args.n, args.ell
     dtype = getattr(torch, args.dtype)
     s = torch.empty((), dtype=dtype).element_size()

@@ -5,6 +5,8 @@
 #if CRB_LO <= 8   // thread-per-node kernels exist only where sizeof(T) * ell^2 <= 256 bytes
 #include "cr_tpn_fwd.cuh"
 #include "cr_tpn_bwd.cuh"
+#include "cr_cs_fwd.cuh"
+#include "cr_cs_bwd.cuh"
 #define CRB_HAVE_TPN 1
 #else
 #define CRB_HAVE_TPN 0
@@ -25,13 +27,31 @@ int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
 int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
 #else
 
+#if CRB_HAVE_TPN
+// lanes per node of the column-split family for (CRB_T, L); 1 = not used
+template <int L>
+struct CsSel {
+  static constexpr int LPN = sizeof(CRB_T) == 4 ? (L == 8 ? 2 : 1) : (L == 8 ? 4 : (L == 4 ? 2 : 1));
+  static constexpr bool FWD = CsFwdCfg<CRB_T, L, (LPN > 1 ? LPN : 2)>::ELIGIBLE && LPN > 1;
+  static constexpr bool BWD = CsBwdCfg<CRB_T, L, (LPN > 1 ? LPN : 2)>::ELIGIBLE && LPN > 1;
+};
+#endif
+
 template <int L>
 struct Dispatch {
   static cudaError_t fwd(int ell, const LevelFwdArgs& a, cudaStream_t s) {
     if (ell == L) {
 #if CRB_HAVE_TPN
+      if constexpr (CsSel<L>::FWD) {
+        // auto: column-split only where the thread-per-node kernel does not exist (measured: at fp32 l=8 the
+        // extra resident warps are paid for by redundant Cholesky work and half-used broadcast reads)
+        if (a.variant == CRB200_COLUMN_SPLIT || (a.variant == CRB200_AUTO && !TpnFwdCfg<CRB_T, L>::ELIGIBLE))
+          return launch_cs_fwd<CRB_T, L, CsSel<L>::LPN>(a, s);
+      } else {
+        if (a.variant == CRB200_COLUMN_SPLIT) return cudaErrorInvalidValue;
+      }
       if constexpr (TpnFwdCfg<CRB_T, L>::ELIGIBLE) {
-        if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_fwd<CRB_T, L>(a, s);
+        if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_fwd<CRB_T, L>(a, s);   // incl. CRB200_COPY_ONLY
       } else
 #endif
       {
@@ -44,6 +64,12 @@ struct Dispatch {
   static cudaError_t bwd(int ell, const LevelBwdArgs& a, cudaStream_t s) {
     if (ell == L) {
 #if CRB_HAVE_TPN
+      if constexpr (CsSel<L>::BWD) {
+        if (a.variant == CRB200_COLUMN_SPLIT || (a.variant == CRB200_AUTO && !TpnBwdCfg<CRB_T, L>::ELIGIBLE))
+          return launch_cs_bwd<CRB_T, L, CsSel<L>::LPN>(a, s);
+      } else {
+        if (a.variant == CRB200_COLUMN_SPLIT) return cudaErrorInvalidValue;
+      }
       if constexpr (TpnBwdCfg<CRB_T, L>::ELIGIBLE) {
         if (a.variant != CRB200_LANE_PER_ROW) return launch_tpn_bwd<CRB_T, L>(a, s);
       } else
@@ -63,6 +89,7 @@ struct Dispatch {
     if (ell != L) return Dispatch<L + 1>::fwd_tile(ell);
 #if CRB_HAVE_TPN
     if (TpnFwdCfg<CRB_T, L>::ELIGIBLE) return TpnFwdCfg<CRB_T, L>::OWN;
+    if (CsSel<L>::FWD) return CsFwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::OWN;
 #endif
     return FwdCfg<CRB_T, L>::NG - 1;
   }
@@ -70,6 +97,7 @@ struct Dispatch {
     if (ell != L) return Dispatch<L + 1>::bwd_tile(ell);
 #if CRB_HAVE_TPN
     if (TpnBwdCfg<CRB_T, L>::ELIGIBLE) return TpnBwdCfg<CRB_T, L>::NT;
+    if (CsSel<L>::BWD) return CsBwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::NT;
 #endif
     return BwdCfg<CRB_T, L>::NG;
   }

@@ -58,7 +58,9 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   const bool halo = a.G_halo != nullptr;
   const int lane = threadIdx.x;
 
-  // ---------------- stage in ----------------
+  // ---------------- stage in: two cp.async groups ----------------
+  // group 0 = factors D, F, G and the vectors (needed first: D^{-1}, P, Q, w); group 1 = S~_d, S~_o of the
+  // deeper level.  The triangular inverse and the P / Q products overlap the arrival of group 1.
   {
     rec_g2s<T, BS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * BS, 0, nE, is_aligned16(a.D));
     const int nF = cmax(0, cmin(NT, o - e0));
@@ -70,6 +72,14 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
       rec_g2s<T, BS, 1>(rec1 + Cf::C * ES, nsb, static_cast<const T*>(a.G_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.G_halo));
     const int ilo = (e0 == 0) ? 1 : 0;
     const int nodd = cmin(e0 + NT, o) - (e0 - 1 + ilo);          // deeper node e0-1+i -> record i
+    if (do_w) {
+      rec_g2s<T, L, 1>(rec1 + Cf::X * ES, nsb, static_cast<const T*>(a.xk) + ((size_t)b * E + e0) * L, 0, nE, is_aligned16(a.xk));
+      rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_in) + ((size_t)b * o + (e0 - 1 + ilo)) * L, ilo, nodd,
+                       is_aligned16(a.w_in));
+      if (e0 == 0 && halo)
+        rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_halo) + (size_t)b * L, 0, 1, is_aligned16(a.w_halo));
+    }
+    cp_async_commit();
     if (do_sigma) {
       rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * BS, ilo, nodd,
                         is_aligned16(a.Sd_in));
@@ -82,17 +92,14 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
           rec_g2s<T, BS, 1>(rec1 + Cf::SO * ES, nsb, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, 0, 1, is_aligned16(a.So_halo_in));
       }
     }
-    if (do_w) {
-      rec_g2s<T, L, 1>(rec1 + Cf::X * ES, nsb, static_cast<const T*>(a.xk) + ((size_t)b * E + e0) * L, 0, nE, is_aligned16(a.xk));
-      rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_in) + ((size_t)b * o + (e0 - 1 + ilo)) * L, ilo, nodd,
-                       is_aligned16(a.w_in));
-      if (e0 == 0 && halo)
-        rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_halo) + (size_t)b * L, 0, 1, is_aligned16(a.w_halo));
-    }
-    cp_async_wait_all();
+    cp_async_commit();
+    cp_async_wait_group<1>();      // factors and vectors have landed
     __syncwarp();
   }
 
+  // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
+  // ceiling of this access pattern
+  if (a.variant != CRB200_COPY_ONLY) {
   // ---------------- per-node compute ----------------
   T* N = S + (size_t)(lane + 1) * NS;     // this node's record
   const T* Lf = S + (size_t)lane * NS;    // left neighbour's record (S~_d[e-1], w~_{e-1})
@@ -201,6 +208,8 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
     if (valid) sts_row<T, L>(N + Cf::X, wv);
   }
 
+  cp_async_wait_group<0>();        // S~_d, S~_o have landed
+  __syncwarp();
   if (do_sigma) {
     // The three big products run as ROLLED loops over a row / column index that only addresses
     // shared memory (P and Q keep static register indices): 8x less code than full unrolling, which
@@ -319,6 +328,10 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   }
   __syncwarp();
 
+  }
+
+  cp_async_wait_group<0>();        // (copy-only path) everything staged
+  __syncwarp();
   // ---------------- stage out ----------------
   const int row_lo = 2 * e0;
   const int nrows = cmin(2 * nE, m - row_lo);

@@ -58,22 +58,73 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   const T* gO = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
   const T* gy = has_y ? static_cast<const T*>(a.y) + (size_t)b * a.stridey : nullptr;
 
-  // ---------------- stage in ----------------
+  // ---------------- stage in: two cp.async groups ----------------
+  // group 0 = R tile + y (needed first: Cholesky, half solve); group 1 = O tile.  The Cholesky of this CTA
+  // overlaps the arrival of group 1, and the factor blocks leave for global memory as soon as they exist,
+  // so one CTA keeps the memory pipe busy through most of its life (only 5 such CTAs fit on an SM).
   {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
     rec_g2s<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, nR, is_aligned16(gR));
+    if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
+    cp_async_commit();
     const int pfirst = (r0 == 0) ? 1 : 0;
     const int nO = cmin(2 * NT - 1, m - r0) - pfirst;
     rec_g2s<T, BS, 2>(s0 + C::OL * ES, nsb, gO + (size_t)(r0 - 1 + pfirst) * BS, pfirst, nO, is_aligned16(gO));
     if (r0 == 0 && halo)
       rec_g2s<T, BS, 2>(s0 + C::OL * ES, nsb, static_cast<const T*>(a.O_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.O_halo));
-    if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
-    cp_async_wait_all();
-    __syncwarp();
+    cp_async_commit();
   }
 
+  // ---------------- stage out, piece by piece ----------------
+  const int n_own = cmin(OWN, E - e0);
+  const int n_odd = cmax(0, cmin(OWN, o - e0));
+  auto out_D_x = [&]() {
+    if (a.D != nullptr)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+    if (a.xk != nullptr && has_y)
+      rec_s2g<T, L, 1>(static_cast<T*>(a.xk) + ((size_t)b * E + e0) * L, s0 + C::YE * ES, nsb, 0, n_own, is_aligned16(a.xk));
+  };
+  auto out_F = [&]() {
+    if (a.D != nullptr)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.F) + ((size_t)b * o + e0) * BS, s0 + C::OR_ * ES, nsb, 0, n_odd, is_aligned16(a.F));
+  };
+  auto out_G = [&]() {
+    if (a.D != nullptr) {
+      const int gfirst = (e0 == 0) ? 1 : 0;
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.G) + ((size_t)b * gcnt + (e0 + gfirst - 1)) * BS, s0 + C::OL * ES, nsb, gfirst, n_own - gfirst,
+                        is_aligned16(a.G));
+    }
+    if (halo && e0 == 0 && a.G_halo != nullptr)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.G_halo) + (size_t)b * BS, s0 + C::OL * ES, nsb, 0, 1, is_aligned16(a.G_halo));
+  };
+  auto out_reduced = [&]() {
+    if (a.Rn != nullptr && n_odd > 0) {
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RO * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+      if (has_y && a.yn != nullptr)
+        rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
+      const int ofirst = (e0 == 0) ? 1 : 0;
+      const int n_on = cmax(0, cmin(e0 + n_own, o) - (e0 + ofirst));
+      if (a.On != nullptr && n_on > 0)
+        rec_s2g<T, BS, 1>(static_cast<T*>(a.On) + ((size_t)b * (o - 1) + (e0 + ofirst - 1)) * BS, s0 + C::ON * ES, nsb, ofirst, n_on,
+                          is_aligned16(a.On));
+    }
+    if (halo && e0 == 0 && a.On_halo != nullptr && o > 0)
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.On_halo) + (size_t)b * BS, s0 + C::ON * ES, nsb, 0, 1, is_aligned16(a.On_halo));
+  };
+
+  // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
+  // ceiling of this access pattern
+  if (a.variant == CRB200_COPY_ONLY) {
+    cp_async_wait_group<0>();
+    __syncwarp();
+    out_D_x(); out_F(); out_G(); out_reduced();
+    return;
+  }
+  {
   // ---------------- per-node compute (everything in registers) ----------------
+  cp_async_wait_group<1>();      // R tile and y have landed
+  __syncwarp();
   T* N = S + (size_t)lane * NS;
   const int e = e0 + lane;
   const bool valid = e < E;
@@ -146,6 +197,10 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       for (int c = 0; c < L; ++c) mh_part += (double)x[c] * (double)x[c];
     }
   }
+  __syncwarp();
+  out_D_x();                     // K and x leave now; the stores overlap the rest of the kernel
+  cp_async_wait_group<0>();      // O tile has landed
+  __syncwarp();
 
   // F = O_right K^{-T} (row by row), A = F F^T (lower), u = F x
   T A[L][L];   // only r >= c used
@@ -180,6 +235,9 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       }
   }
 
+  __syncwarp();
+  out_F();                       // F is final in shared memory
+
   // G = O_left^T K^{-T}: row r of G solves against column r of O_left
   T G[L][L];
   {
@@ -205,6 +263,8 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       for (int r = 0; r < L; ++r) sts_row<T, L>(N + C::OL + r * L, G[r]);
     }
   }
+  __syncwarp();
+  out_G();                       // G is final in shared memory
 
   // O~_{e-1} = -F G^T (F rows re-read from shared memory), B = G G^T (lower), v = G x
   if (do_f && has_left) {
@@ -297,34 +357,9 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   }
   __syncwarp();
 
-  // ---------------- stage out ----------------
-  const int n_own = cmin(OWN, E - e0);
-  const int n_odd = cmax(0, cmin(OWN, o - e0));
-  if (a.D != nullptr) {
-    rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
-    rec_s2g<T, BS, 1>(static_cast<T*>(a.F) + ((size_t)b * o + e0) * BS, s0 + C::OR_ * ES, nsb, 0, n_odd, is_aligned16(a.F));
-    const int gfirst = (e0 == 0) ? 1 : 0;
-    rec_s2g<T, BS, 1>(static_cast<T*>(a.G) + ((size_t)b * gcnt + (e0 + gfirst - 1)) * BS, s0 + C::OL * ES, nsb, gfirst, n_own - gfirst,
-                      is_aligned16(a.G));
   }
-  if (a.xk != nullptr && has_y)
-    rec_s2g<T, L, 1>(static_cast<T*>(a.xk) + ((size_t)b * E + e0) * L, s0 + C::YE * ES, nsb, 0, n_own, is_aligned16(a.xk));
-  if (a.Rn != nullptr && n_odd > 0) {
-    rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RO * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
-    if (has_y && a.yn != nullptr)
-      rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
-    const int ofirst = (e0 == 0) ? 1 : 0;
-    const int n_on = cmax(0, cmin(e0 + n_own, o) - (e0 + ofirst));
-    if (a.On != nullptr && n_on > 0)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.On) + ((size_t)b * (o - 1) + (e0 + ofirst - 1)) * BS, s0 + C::ON * ES, nsb, ofirst, n_on,
-                        is_aligned16(a.On));
-  }
-  if (halo && e0 == 0) {
-    if (a.G_halo != nullptr)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.G_halo) + (size_t)b * BS, s0 + C::OL * ES, nsb, 0, 1, is_aligned16(a.G_halo));
-    if (a.On_halo != nullptr && o > 0)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.On_halo) + (size_t)b * BS, s0 + C::ON * ES, nsb, 0, 1, is_aligned16(a.On_halo));
-  }
+
+  out_reduced();                 // R~, y~, O~ (and the halo coupling)
 }
 
 template <typename T, int L>

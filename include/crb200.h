@@ -29,10 +29,13 @@ extern "C" {
 #define CRB200_F32 0
 #define CRB200_F64 1
 
-/* kernel families: lane-per-row (any ell <= 32) and thread-per-node (sizeof(T)*ell*ell <= 256 B) */
+/* kernel families: lane-per-row (any ell <= 32), thread-per-node (sizeof(T)*ell*ell <= 256 B) and
+ * column-split (several lanes per node: fp32 ell=8, fp64 ell=4 and 8) */
 #define CRB200_AUTO 0
 #define CRB200_LANE_PER_ROW 1
 #define CRB200_THREAD_PER_NODE 2
+#define CRB200_COLUMN_SPLIT 3
+#define CRB200_COPY_ONLY 99       /* profiling aid (thread-per-node kernels): stage in / out only, results are garbage */
 
 #define CRB200_OK 0
 #define CRB200_EINVAL (-1)        /* null / inconsistent argument                      */
