@@ -97,6 +97,35 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
     __syncwarp();
   }
 
+  // ---------------- stage out, piece by piece ----------------
+  const int row_lo = 2 * e0;
+  const int nrows = cmin(2 * nE, m - row_lo);
+  const int so_plo = (e0 == 0) ? 1 : 0;
+  const int nso_rows = cmin(2 * e0 + 2 * nE - 1, m - 1) - (2 * e0 - 1 + so_plo);
+  auto out_Sd = [&]() {
+    if (do_sigma) {
+      T* Sd = static_cast<T*>(a.Sd_out) + (size_t)b * a.strideSd;
+      rec_s2g<T, BS, 2>(Sd + (size_t)row_lo * BS, rec1 + Cf::A * ES, nsb, 0, nrows, is_aligned16(Sd));
+    }
+  };
+  auto out_So = [&]() {
+    if (do_sigma) {
+      if (nso_rows > 0) {
+        T* So = static_cast<T*>(a.So_out) + (size_t)b * a.strideSo;
+        rec_s2g<T, BS, 2>(So + (size_t)(2 * e0 - 1 + so_plo) * BS, rec1 + Cf::C * ES, nsb, so_plo, nso_rows, is_aligned16(So));
+      }
+      if (e0 == 0 && halo && a.So_halo_out != nullptr)
+        rec_s2g<T, BS, 1>(static_cast<T*>(a.So_halo_out) + (size_t)b * BS, rec1 + Cf::C * ES, nsb, 0, 1, is_aligned16(a.So_halo_out));
+    }
+  };
+  auto out_w = [&]() {
+    if (do_w) {
+      T* W = static_cast<T*>(a.w_out) + (size_t)b * a.stridew;
+      rec_s2g<T, L, 2>(W + (size_t)row_lo * L, rec1 + Cf::X * ES, nsb, 0, nrows, is_aligned16(W));
+    }
+  };
+  const bool early = (a.grad_mode == 0) && (a.variant != CRB200_COPY_ONLY);   // inner levels: results are final as produced
+
   // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
   // ceiling of this access pattern
   if (a.variant != CRB200_COPY_ONLY) {
@@ -251,6 +280,11 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         for (int r = 0; r < L; ++r) N[Cf::C + r * L + c] = st[r];
       }
     }
+    if (early) {
+      __syncwarp();
+      out_So();                    // Sigma_off rows and w are final: let them leave while Sigma_{2e,2e} is computed
+      out_w();
+    }
     // Sigma_{2e,2e} = Di^T Di - S_d^T P - (S_o^T) Q, row by row in place in A:
     // row r needs column r of S_d (B) and row r of Sigma_{2e,2e-1} (C)
     if (valid) {
@@ -332,24 +366,11 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 
   cp_async_wait_group<0>();        // (copy-only path) everything staged
   __syncwarp();
-  // ---------------- stage out ----------------
-  const int row_lo = 2 * e0;
-  const int nrows = cmin(2 * nE, m - row_lo);
-  const int so_plo = (e0 == 0) ? 1 : 0;
-  const int nso_rows = cmin(2 * e0 + 2 * nE - 1, m - 1) - (2 * e0 - 1 + so_plo);
-  if (do_sigma) {
-    T* Sd = static_cast<T*>(a.Sd_out) + (size_t)b * a.strideSd;
-    rec_s2g<T, BS, 2>(Sd + (size_t)row_lo * BS, rec1 + Cf::A * ES, nsb, 0, nrows, is_aligned16(Sd));
-    if (nso_rows > 0) {
-      T* So = static_cast<T*>(a.So_out) + (size_t)b * a.strideSo;
-      rec_s2g<T, BS, 2>(So + (size_t)(2 * e0 - 1 + so_plo) * BS, rec1 + Cf::C * ES, nsb, so_plo, nso_rows, is_aligned16(So));
-    }
-    if (e0 == 0 && halo && a.So_halo_out != nullptr)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.So_halo_out) + (size_t)b * BS, rec1 + Cf::C * ES, nsb, 0, 1, is_aligned16(a.So_halo_out));
-  }
-  if (do_w) {
-    T* W = static_cast<T*>(a.w_out) + (size_t)b * a.stridew;
-    rec_s2g<T, L, 2>(W + (size_t)row_lo * L, rec1 + Cf::X * ES, nsb, 0, nrows, is_aligned16(W));
+  // ---------------- stage out (what has not left yet) ----------------
+  out_Sd();
+  if (!early || !do_sigma) {
+    out_So();
+    out_w();
   }
 }
 

@@ -170,6 +170,40 @@ def test_full_path_vs_oracle(l, n, dtype):
     assert_close(xr.grad, gx, tol, "gx")
 
 
+@pytest.mark.parametrize("l,n,dtype,variant", [
+    (8, 2050, torch.float32, 1), (8, 2050, torch.float32, 2), (8, 2050, torch.float32, 3),      # lane-per-row / thread-per-node / column-split
+    (8, 777, torch.float64, 1), (8, 777, torch.float64, 3),
+    (4, 1500, torch.float64, 1), (4, 1500, torch.float64, 2), (4, 1500, torch.float64, 3),
+    (4, 3001, torch.float32, 1), (4, 3001, torch.float32, 2),
+    (3, 500, torch.float64, 1), (3, 500, torch.float64, 2), (5, 300, torch.float32, 1), (5, 300, torch.float32, 2)])
+def test_every_kernel_family_vs_oracle(l, n, dtype, variant):
+    """The same contract is implemented by up to three kernel families (include/crb200.h, `variant`);
+    force each one and compare the whole path (forward, backward, selected inverse, solve) with the oracle."""
+    from cyclic_gps import _native
+    c = cr()
+    tol = TOL[dtype]
+    R, O, x = leg_inputs(l, n, dtype, seed=3 * l + n + variant)
+    Rd, Od, xd = R.double(), O.double(), x.double()
+    dec_o = orc.factor(Rd, Od)
+    _native.VARIANT = variant
+    try:
+        Rr, Or, xr = [t.cuda().requires_grad_(True) for t in (R, O, x)]
+        mm, dd = c.mahal_and_det(Rr, Or, xr)
+        (1.25 * mm + 0.75 * dd).backward()
+        dec = c.decompose(R.cuda(), O.cuda())
+        w = c.solve(dec, x.cuda())
+        Sd, So = c.inverse_blocks(dec)
+    finally:
+        _native.VARIANT = 0
+    gR, gO, gx = orc.loglik_grads(Rd, Od, xd, 1.25, 0.75)
+    Sd_o, So_o = orc.selected_inverse(dec_o)
+    for got, want, name in ((mm, orc.mahal(dec_o, xd), "mahal"), (dd, orc.logdet(dec_o), "logdet"), (w, orc.solve(dec_o, xd), "solve"),
+                            (Sd, Sd_o, "Sigma diag"), (So, So_o, "Sigma off"), (Rr.grad, gR, "gR"), (Or.grad, gO, "gO"), (xr.grad, gx, "gx")):
+        assert_close(got, want, tol, f"{name} (variant {variant})")
+    for k, (a, b) in enumerate(zip(dec[1], dec_o[1])):
+        assert_close(a, b, tol, f"D[{k}] (variant {variant})")
+
+
 def test_det_of_decompose_is_differentiable():
     c = cr()
     R, O, _ = leg_inputs(4, 300, torch.float64, seed=5)
