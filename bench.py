@@ -170,6 +170,10 @@ def cpu_reference_rows_per_s(n, ell, dtype, series, repeats=1, warm=1):
     return series * n / best, best
 
 
+def workload_name(B, n, ell, dtype_name):
+    return f"configs[1]: batched LEG loglik+grad, {B} series x n={n}, l={ell}, {dtype_name}, batch-sharded"
+
+
 def run_reference(args):
     """--impl reference: the reference CPU implementation of the path (oracle port of
     cyclic_reduction.py + torch autograd, all host threads), bounded sample per step."""
@@ -190,8 +194,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: LEG loglik+grad, n=10^4, l=8, fp32 (reference CPU path, oracle port)",
-                       "batch_per_step": series_per_step, "n": n, "ell": ell},
+            "config": {"workload": workload_name(WORKLOAD["batch"], n, ell, WORKLOAD["dtype"]),
+                       "batch_per_gpu": WORKLOAD["batch"], "n": n, "ell": ell,
+                       "reference_sample": f"{series_per_step} of {WORKLOAD['batch']} series per step, reference CPU path (oracle port), "
+                                           "one series at a time"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -518,7 +524,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-            "config": {"workload": f"configs[1]: batched LEG loglik+grad, {B} series x n={n}, l={ell}, {args.dtype}, batch-sharded",
+            "config": {"workload": workload_name(B, n, ell, args.dtype),
                        "batch_per_gpu": B, "n": n, "ell": ell, "parallelism": f"batch-shard x{world}",
                        "l2": "inputs per step (%.1f GB) exceed L2 (126 MB); no explicit flush" % ((R.numel() + O.numel() + x.numel()) * s / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

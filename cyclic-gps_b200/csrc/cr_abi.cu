@@ -105,7 +105,7 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
   l.batch = a->batch;
   l.R = a->R; l.O = a->O; l.y = a->y;
   l.strideR = a->strideR; l.strideO = a->strideO; l.stridey = a->stridey;
-  l.logdet = a->logdet; l.mahal = a->mahal;
+  l.logdet = a->logdet; l.mahal = a->mahal; l.acc_slots = a->acc_slots;
   l.Rh_acc = a->Rh_acc; l.yh_acc = a->yh_acc; l.variant = a->variant;
   const void* halo = a->O_halo;
   long long offE = 0, offO = 0, offG = 0;

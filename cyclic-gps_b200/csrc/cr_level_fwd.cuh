@@ -30,6 +30,12 @@ namespace crb200 {
 
 using LevelFwdArgs = ::crb200_fwd_args;   // include/crb200.h
 
+// slot of the per-series scalar accumulators this CTA adds into (see crb200_fwd_args.acc_slots)
+__device__ __forceinline__ size_t acc_index(const LevelFwdArgs& a, int b, int tile) {
+  const int slots = a.acc_slots > 0 ? a.acc_slots : 1;
+  return (size_t)b * slots + (tile % slots);
+}
+
 template <typename T, int L>
 struct FwdCfg {
   static constexpr int LG = GroupLanes<L>::value;
@@ -237,11 +243,11 @@ cr_level_fwd_kernel(const LevelFwdArgs a) {
   // scalars: one atomic per CTA per accumulator
   if (a.logdet != nullptr) {
     const double t = block_sum(ld_part, sred);
-    if (threadIdx.x == 0) atomicAdd(a.logdet + b, t);
+    if (threadIdx.x == 0) atomicAdd(a.logdet + acc_index(a, b, tile), t);
   }
   if (a.mahal != nullptr && has_y) {
     const double t = block_sum(mh_part, sred);
-    if (threadIdx.x == 0) atomicAdd(a.mahal + b, t);
+    if (threadIdx.x == 0) atomicAdd(a.mahal + acc_index(a, b, tile), t);
   }
   __syncthreads();
 

@@ -348,12 +348,12 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   if (a.logdet != nullptr) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ld_part += __shfl_xor_sync(0xffffffffu, ld_part, off);
-    if (lane == 0) atomicAdd(a.logdet + b, ld_part);
+    if (lane == 0) atomicAdd(a.logdet + acc_index(a, b, tile), ld_part);
   }
   if (a.mahal != nullptr && has_y) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mh_part += __shfl_xor_sync(0xffffffffu, mh_part, off);
-    if (lane == 0) atomicAdd(a.mahal + b, mh_part);
+    if (lane == 0) atomicAdd(a.mahal + acc_index(a, b, tile), mh_part);
   }
   __syncwarp();
 

@@ -17,6 +17,9 @@ import torch
 from . import _native
 
 
+ACC_SLOTS = 32
+
+
 class NotPositiveDefiniteError(RuntimeError):
     """Raised when a diagonal block met during elimination is not positive definite
     (the reference raises gpytorch's NotPSDError after its jitter ladder,
@@ -135,8 +138,10 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
     else:
         pack.X_flat = None
         pack.X = [None] * L
-    pack.logdet = torch.zeros(B, dtype=torch.float64, device=dev) if want_logdet else None
-    pack.mahal = torch.zeros(B, dtype=torch.float64, device=dev) if y is not None else None
+    # scalar accumulators: (B, ACC_SLOTS) so that the per-CTA atomics of a long series do not all hit one address
+    slots = ACC_SLOTS if n >= 4096 else 1
+    acc_ld = torch.zeros((B, slots), dtype=torch.float64, device=dev) if want_logdet else None
+    acc_mh = torch.zeros((B, slots), dtype=torch.float64, device=dev) if y is not None else None
     pack.info = torch.zeros(L, dtype=torch.int32, device=dev)
     halo = halo_O is not None
     Rh = yh = None
@@ -165,7 +170,7 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
                           strideR=sR, strideO=sO, stridey=sy,
                           D=pack.D_flat, F=pack.F_flat if (keep_factors and pack.F_flat.numel()) else None,
                           G=pack.G_flat if (keep_factors and pack.G_flat.numel()) else None, X=pack.X_flat,
-                          scrR=scrR, scrO=scrO, scry=scry, logdet=pack.logdet, mahal=pack.mahal, info=pack.info,
+                          scrR=scrR, scrO=scrO, scry=scry, logdet=acc_ld, mahal=acc_mh, acc_slots=slots, info=pack.info,
                           O_halo=halo_O, G_halo=pack.G_halo_flat, On_halo=On_h, Rh_acc=Rh, yh_acc=yh)
     else:
         cur_R, cur_O, cur_y, cur_halo = R, O, y, halo_O
@@ -177,15 +182,15 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
                           D=pack.D[k], F=pack.F[k] if o > 0 else None, G=pack.G[k] if g > 0 else None, xk=pack.X[k],
                           Rn=scrR[slot] if o > 0 else None, On=scrO[slot] if o > 1 else None,
                           yn=scry[slot] if (o > 0 and y is not None) else None,
-                          logdet=pack.logdet, mahal=pack.mahal, info=pack.info[k:k + 1])
+                          logdet=acc_ld, mahal=acc_mh, acc_slots=slots, info=pack.info[k:k + 1])
             if halo:
                 fields.update(O_halo=cur_halo, G_halo=pack.G_halo[k] if keep_factors else None, On_halo=On_h[slot], Rh_acc=Rh, yh_acc=yh)
                 cur_halo = On_h[slot]
             _native.level_fwd(dtype, ell, **fields)
             cur_R, cur_O, cur_y = fields["Rn"], fields["On"], fields["yn"]
             sR, sO, sy = o * bs, max(o - 1, 0) * bs, o * ell
-    if pack.logdet is not None:
-        pack.logdet.mul_(2.0)    # log|J| = 2 sum log diag(K)   (reference det :458, mahal_and_det :438)
+    pack.mahal = acc_mh.sum(dim=1) if acc_mh is not None else None
+    pack.logdet = acc_ld.sum(dim=1).mul_(2.0) if acc_ld is not None else None   # log|J| = 2 sum log diag(K)  (reference :458, :438)
     last = (L - 1) & 1
     if L < len(ms_all):
         o = ms[-1] // 2

@@ -27,7 +27,7 @@ class FwdArgs(C.Structure):
                 ("strideR", _ll), ("strideO", _ll), ("stridey", _ll),
                 ("D", _vp), ("F", _vp), ("G", _vp), ("xk", _vp),
                 ("Rn", _vp), ("On", _vp), ("yn", _vp),
-                ("logdet", _vp), ("mahal", _vp), ("info", _vp),
+                ("logdet", _vp), ("mahal", _vp), ("acc_slots", _i), ("info", _vp),
                 ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp), ("variant", _i)]
 
 
@@ -54,7 +54,7 @@ class SweepFwdArgs(C.Structure):
                 ("strideR", _ll), ("strideO", _ll), ("stridey", _ll),
                 ("D", _vp), ("F", _vp), ("G", _vp), ("X", _vp),
                 ("scrR", _vp * 2), ("scrO", _vp * 2), ("scry", _vp * 2),
-                ("logdet", _vp), ("mahal", _vp), ("info", _vp),
+                ("logdet", _vp), ("mahal", _vp), ("info", _vp), ("acc_slots", _i),
                 ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp * 2), ("Rh_acc", _vp), ("yh_acc", _vp),
                 ("variant", _i)]
 

@@ -53,7 +53,9 @@ typedef struct crb200_fwd_args {
                                                          => factors not kept; xk NULL => not stored  */
   void* Rn; void* On; void* yn;                       /* out: reduced system (batch,o,..),(batch,o-1,..),(batch,o,l) */
   double* logdet; double* mahal;                      /* in/out per-series accumulators (+= sum log diag K,
-                                                         += |x_k|^2), NULL to skip                   */
+                                                         += |x_k|^2), NULL to skip; each is (batch, acc_slots) */
+  int acc_slots;                                      /* >= 1 (0 = 1): a CTA adds into slot (tile mod acc_slots), which
+                                                         spreads the atomics of long series over several addresses  */
   int* info;                                          /* in/out: max over failures of INT_MAX - (series*E + e);
                                                          caller zero-initialises; 0 = all blocks PD  */
   /* left halo (chunk-partitioned series): virtual surviving node -1 coupled to row 0 by O_halo */
@@ -104,6 +106,7 @@ typedef struct crb200_sweep_fwd_args {
   void* D; void* F; void* G; void* X;                 /* packed factors; D/F/G NULL => not kept; X NULL => x_k not kept */
   void* scrR[2]; void* scrO[2]; void* scry[2];        /* [0] >= batch*floor(n/2) rows, [1] >= batch*floor(n/4) rows */
   double* logdet; double* mahal; int* info;           /* info: nlevels ints, zero-initialised by the caller */
+  int acc_slots;                                      /* logdet / mahal are (batch, acc_slots), see crb200_fwd_args */
   const void* O_halo; void* G_halo;                   /* G_halo: nlevels * batch blocks (NULL => not kept) */
   void* On_halo[2]; void* Rh_acc; void* yh_acc;
   int variant;
