@@ -80,3 +80,31 @@ def _worker(rank, world, port):
 def test_chunked_world2_shared_gpu():
     port = 29700 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_long_series_full_size_properties():
+    """n = 4e6, l = 4, fp32 (what fits a quick test; the bench runs n = 1e8): the chunked path must agree with the
+    plain single-sweep path, the solve must satisfy J w = x, and gx = 2 w."""
+    from cyclic_gps import cyclic_reduction as c, distributed as D
+    from cyclic_gps.synth import gaps_for_rows, leg_params, leg_precision_rows
+    from helpers import relerr
+    n, l = 4_000_000, 4
+    dev = torch.device("cuda")
+    G, Bm, LLT = leg_params(l, seed=0, device=dev)
+    R, Oprev = leg_precision_rows(gaps_for_rows(0, n, n, seed=5, device=dev), G, Bm, LLT, torch.float32)
+    x = torch.randn((n, l), dtype=torch.float32, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    O = Oprev[1:].contiguous()
+    mm, dd = c.mahal_and_det(R, O, x)
+    plan = D.make_plan(n, 1, sub=1 << 16)
+    Rl, Ol, xl = R.clone().requires_grad_(True), Oprev.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    mc, dc = D.chunked_mahal_and_det(Rl, Ol, xl, plan, 0)
+    assert relerr(mc, mm) < 1e-5 and relerr(dc, dd) < 1e-5
+    mc.backward()
+    dec = c.decompose(R, O)
+    w = c.solve(dec, x)
+    assert relerr(xl.grad, 2 * w) < 1e-4
+    Jw = torch.einsum("nij,nj->ni", R.double(), w.double())
+    Jw[1:] += torch.einsum("nij,nj->ni", O.double(), w[:-1].double())
+    Jw[:-1] += torch.einsum("nji,nj->ni", O.double(), w[1:].double())
+    assert float((Jw - x.double()).abs().max() / x.abs().max()) < 1e-4
+    assert relerr(mm, (x.double() * w.double()).sum()) < 1e-5

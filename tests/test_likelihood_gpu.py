@@ -61,3 +61,59 @@ def test_log_marginal_likelihood_like_the_reference_test():
                     kf_ll = kf_log_marginal_likelihood(kf, xs)
                     assert torch.allclose(leg, torch.from_numpy(np.array(kf_ll)))
                 assert torch.allclose(leg, naive.reshape(()))
+
+
+def test_model_resident_on_the_gpu(golden):
+    """The same model with parameters, time stamps and data on the device: no host round trips inside
+    log_likelihood; values and parameter gradients must still match the reference."""
+    g = golden["leg_model"]
+    for p in ("irregular_n33_d2_", "regular_n33_d1_"):
+        d = int(p.split("_d")[1][0])
+        m = _model_from_golden(g, p, d).cuda()
+        m.register_model_matrices_from_params()
+        ts, xs = torch.from_numpy(g[p + "ts"]).cuda(), torch.from_numpy(g[p + "xs"]).cuda()
+        ll = m.log_likelihood(ts=ts, xs=xs)
+        assert ll.is_cuda
+        assert_close(ll, g[p + "ll"], 1e-10, p + "loglik on device")
+        ll.backward()
+        for name in ("N_params", "R_params", "Lambda_params", "B"):
+            assert_close(getattr(m, name).grad, g[p + "grad_" + name], 1e-8, p + "grad " + name)
+
+
+def test_co2_shaped_training_step():
+    """BASELINE config 3 shape: n = 502 with a 240-unit gap mid-series, rank 16, fp64, obs_dim 1: one training step
+    (loss + backward through both CR factorisations) and the in-sample posterior, on the device, against the
+    same model evaluated with the CPU oracle for the CR calls."""
+    import math
+    from cyclic_gps.models import LEGFamily
+    from oracle import cr_oracle as orc
+    torch.manual_seed(3)
+    n, rank = 502, 16
+    gaps = torch.ones(n - 1, dtype=torch.float64)
+    gaps[261] = 240.0
+    ts = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(gaps, 0)]) / 12.0
+    xs = torch.randn(n, 1, dtype=torch.float64)
+    model = LEGFamily(rank=rank, obs_dim=1, train=True, data_type=torch.float64)
+    loss = model.training_step((ts.unsqueeze(0), xs.unsqueeze(0)), 0)
+    loss.backward()
+    # oracle evaluation of the same likelihood (CPU, torch autograd through the oracle)
+    ref = LEGFamily(rank=rank, obs_dim=1, train=True, data_type=torch.float64)
+    ref.load_state_dict(model.state_dict())
+    ref.register_model_matrices_from_params()
+    LLT, shift = ref._obs_terms()
+    white = torch.linalg.solve(LLT, xs.T).T
+    Rs, Os = ref.compute_PEG_precision(ts)
+    mh, ld = orc.mahal_and_logdet(Rs + shift.unsqueeze(0), Os, white @ ref.B)
+    prior = orc.logdet(orc.factor(Rs, Os))
+    ll = -0.5 * ((torch.sum(white * xs) - mh) + (torch.logdet(2 * math.pi * LLT) * n + ld - prior))
+    (-ll / n).backward()
+    assert_close(loss, -ll / n, 1e-10, "loss")
+    for name in ("N_params", "R_params", "Lambda_params", "B"):
+        assert_close(getattr(model, name).grad, getattr(ref, name).grad, 1e-8, "grad " + name)
+    with torch.no_grad():
+        mean, cov = model.compute_insample_posterior(ts, xs)
+        dec = orc.factor(*ref.compute_posterior_precision(ts))
+        assert_close(mean, orc.solve(dec, ref.compute_v(xs)), 1e-9, "posterior mean")
+        sd, so = orc.selected_inverse(dec)
+        assert_close(cov["Rs"], sd, 1e-9, "posterior cov diag")
+        assert_close(cov["Os"], so, 1e-9, "posterior cov off")
