@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "build")
 STAMP = os.path.join(HERE, "libcrb200.stamp")
 RANGES = [(1, 4), (5, 8), (9, 12), (13, 16), (17, 20), (21, 24), (25, 28), (29, 32)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+              "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC] + os.environ.get("CRB200_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

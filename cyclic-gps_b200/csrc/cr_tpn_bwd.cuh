@@ -29,19 +29,22 @@ struct TpnBwdCfg {
   static constexpr int A = 0, SD = BS, C = 2 * BS, B = 3 * BS, SO = 4 * BS, X = 5 * BS, WT = 5 * BS + L;
   static constexpr int RAW = 5 * BS + 2 * L;
   static constexpr int NS = record_stride<T>(RAW);
-  static constexpr size_t SMEM = (size_t)(NT + 1) * NS * sizeof(T);
+  static constexpr size_t SMEM_W = (size_t)(NT + 1) * NS * sizeof(T);           // per warp
+  static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
+  static constexpr size_t SMEM = SMEM_W * NW;
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
 };
 
 
 template <typename T, int L>
-__global__ void __launch_bounds__(32, TpnBwdCfg<T, L>::MIN_CTAS)
+__global__ void __launch_bounds__(32 * TpnBwdCfg<T, L>::NW, TpnBwdCfg<T, L>::MIN_CTAS)
 cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   using Cf = TpnBwdCfg<T, L>;
   constexpr int BS = Cf::BS, NS = Cf::NS, NT = Cf::NT;
   constexpr unsigned ES = sizeof(T);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* S = reinterpret_cast<T*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  T* S = reinterpret_cast<T*>(smem_raw + (size_t)warp * TpnBwdCfg<T, L>::SMEM_W);
   const unsigned s0 = smem_u32(S);
   const unsigned nsb = NS * ES;
   const unsigned rec1 = s0 + nsb;
@@ -49,14 +52,16 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   const int m = a.m;
   const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
   const int tiles = (E + NT - 1) / NT;
-  const int b = blockIdx.x / tiles;
-  const int tile = blockIdx.x - b * tiles;
+  const long long vb = (long long)blockIdx.x * TpnBwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
+  if (vb >= (long long)tiles * a.batch) return;
+  const int b = (int)(vb / tiles);
+  const int tile = (int)(vb - (long long)b * tiles);
   const int e0 = tile * NT;
   const int nE = cmin(NT, E - e0);
   const bool do_sigma = a.Sd_out != nullptr;
   const bool do_w = a.w_out != nullptr;
   const bool halo = a.G_halo != nullptr;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
 
   // ---------------- stage in: two cp.async groups ----------------
   // group 0 = factors D, F, G and the vectors (needed first: D^{-1}, P, Q, w); group 1 = S~_d, S~_o of the
@@ -387,10 +392,11 @@ cudaError_t launch_tpn_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   }
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::NT - 1) / C::NT;
-  const long long grid = tiles * a.batch;
-  if (grid <= 0) return cudaSuccess;
+  const long long total = tiles * a.batch;
+  if (total <= 0) return cudaSuccess;
+  const long long grid = (total + C::NW - 1) / C::NW;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  cr_tpn_bwd_kernel<T, L><<<(unsigned)grid, 32, C::SMEM, stream>>>(a);
+  cr_tpn_bwd_kernel<T, L><<<(unsigned)grid, 32 * C::NW, C::SMEM, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,10 @@
 #pragma once
 #include "cr_common.cuh"
 
+#ifndef CRB200_TPN_WARPS
+#define CRB200_TPN_WARPS 1     // independent single-tile warps per CTA of the thread-per-node kernels
+#endif
+
 namespace crb200 {
 
 __device__ __forceinline__ void cp_async16_u32(unsigned saddr, const void* gmem) {

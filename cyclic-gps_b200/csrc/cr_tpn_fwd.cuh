@@ -29,17 +29,21 @@ struct TpnFwdCfg {
   static constexpr int RE = 0, RO = BS, OL = 2 * BS, OR_ = 3 * BS, ON = 4 * BS, YE = 5 * BS, YO = 5 * BS + L;
   static constexpr int RAW = 5 * BS + 2 * L;
   static constexpr int NS = record_stride<T>(RAW);
-  static constexpr size_t SMEM = (size_t)NT * NS * sizeof(T);
-  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((220 * 1024) / (SMEM + 1024))));
+  static constexpr size_t SMEM_W = (size_t)NT * NS * sizeof(T);                 // per warp
+  // independent warps per CTA (each warp = one tile): warps of a CTA run the same code at about the same time
+  static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
+  static constexpr size_t SMEM = SMEM_W * NW;
+  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((224 * 1024) / (SMEM + 1024))));
 };
 
 template <typename T, int L>
-__global__ void __launch_bounds__(32, TpnFwdCfg<T, L>::MIN_CTAS)
+__global__ void __launch_bounds__(32 * TpnFwdCfg<T, L>::NW, TpnFwdCfg<T, L>::MIN_CTAS)
 cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   using C = TpnFwdCfg<T, L>;
   constexpr int BS = C::BS, NS = C::NS, NT = C::NT, OWN = C::OWN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* S = reinterpret_cast<T*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  T* S = reinterpret_cast<T*>(smem_raw + (size_t)warp * TpnFwdCfg<T, L>::SMEM_W);
   constexpr unsigned ES = sizeof(T);
   const unsigned s0 = smem_u32(S);
   const unsigned nsb = NS * ES;
@@ -47,12 +51,14 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   const int m = a.m;
   const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
   const int tiles = (E + OWN - 1) / OWN;
-  const int b = blockIdx.x / tiles;
-  const int tile = blockIdx.x - b * tiles;
+  const long long vb = (long long)blockIdx.x * TpnFwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
+  if (vb >= (long long)tiles * a.batch) return;
+  const int b = (int)(vb / tiles);
+  const int tile = (int)(vb - (long long)b * tiles);
   const int e0 = tile * OWN;
   const bool has_y = a.y != nullptr;
   const bool halo = a.O_halo != nullptr;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
 
   const T* gR = static_cast<const T*>(a.R) + (size_t)b * a.strideR;
   const T* gO = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
@@ -375,10 +381,11 @@ cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   }
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::OWN - 1) / C::OWN;
-  const long long grid = tiles * a.batch;
-  if (grid <= 0) return cudaSuccess;
+  const long long total = tiles * a.batch;
+  if (total <= 0) return cudaSuccess;
+  const long long grid = (total + C::NW - 1) / C::NW;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  cr_tpn_fwd_kernel<T, L><<<(unsigned)grid, 32, C::SMEM, stream>>>(a);
+  cr_tpn_fwd_kernel<T, L><<<(unsigned)grid, 32 * C::NW, C::SMEM, stream>>>(a);
   return cudaGetLastError();
 }
 
