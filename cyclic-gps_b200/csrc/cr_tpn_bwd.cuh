@@ -149,6 +149,15 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
     gd = (T)(a.gd != nullptr ? a.gd[b] : 0.0);
   }
 
+  // neutral operands for boundary lanes (rare, hence divergent code is fine): no node -> D = I; no odd
+  // neighbour -> F = 0, w~_e = 0; no left link -> G = 0 (and the never-loaded left record is cleared)
+  if (!valid) smem_fill_identity<T, L>(N + Cf::A);
+  if (!has_odd) { smem_fill_zero<T, BS>(N + Cf::B); smem_fill_zero<T, L>(N + Cf::WT); }
+  if (!has_left) smem_fill_zero<T, BS>(N + Cf::C);
+  if (!valid) smem_fill_zero<T, L>(N + Cf::X);
+  if (lane == 0 && e0 == 0 && !halo) { smem_fill_zero<T, L>(S + Cf::WT); }
+  __syncwarp();
+
   T P[L][L], Q[L][L];
   T dxs[L];
   {
@@ -159,7 +168,7 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
       T row[L];
       lds_row<T, L>(row, N + Cf::A + r * L);
 #pragma unroll
-      for (int c = 0; c < L; ++c) Di[r][c] = valid ? row[c] : (r == c ? T(1) : T(0));   // holds K for now
+      for (int c = 0; c < L; ++c) Di[r][c] = row[c];   // holds K for now
     }
     T dinv[L];
 #pragma unroll
@@ -220,8 +229,8 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         T sp = T(0), sq = T(0);
 #pragma unroll
         for (int k = c; k < L; ++k) { sp = fma(f[k], Di[k][c], sp); sq = fma(g[k], Di[k][c], sq); }
-        P[r][c] = has_odd ? sp : T(0);
-        Q[r][c] = has_left ? sq : T(0);
+        P[r][c] = sp;
+        Q[r][c] = sq;
       }
       sched_fence();
     }
@@ -236,7 +245,7 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
     for (int c = 0; c < L; ++c) {
       T s = dxs[c];
 #pragma unroll
-      for (int k = 0; k < L; ++k) { s = fma(-P[k][c], has_odd ? we[k] : T(0), s); s = fma(-Q[k][c], has_left ? wl[k] : T(0), s); }
+      for (int k = 0; k < L; ++k) { s = fma(-P[k][c], we[k], s); s = fma(-Q[k][c], wl[k], s); }
       wv[c] = s;
     }
     if (valid) sts_row<T, L>(N + Cf::X, wv);
@@ -245,6 +254,9 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   cp_async_wait_group<0>();        // S~_d, S~_o have landed
   __syncwarp();
   if (do_sigma) {
+    if (!has_so) smem_fill_zero<T, BS>(N + Cf::SO);
+    if (lane == 0 && e0 == 0 && !halo) smem_fill_zero<T, BS>(S + Cf::SD);
+    __syncwarp();
     // The three big products run as ROLLED loops over a row / column index that only addresses
     // shared memory (P and Q keep static register indices): 8x less code than full unrolling, which
     // matters because five single-warp CTAs at different program counters share one SM's i-cache.
@@ -260,7 +272,7 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < L; ++k) {
           axpy_row<T, L>(out, -sig[k], P[k]);
-          axpy_row<T, L>(out, has_so ? -so[k] : T(0), Q[k]);
+          axpy_row<T, L>(out, -so[k], Q[k]);
         }
         sts_row<T, L>(N + Cf::B + r * L, out);
       }
@@ -273,7 +285,7 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         T a0[L], socol[L], st[L];
         lds_row<T, L>(a0, Lf + Cf::SD + c * L);
 #pragma unroll
-        for (int k = 0; k < L; ++k) socol[k] = has_so ? N[Cf::SO + k * L + c] : T(0);
+        for (int k = 0; k < L; ++k) socol[k] = N[Cf::SO + k * L + c];
 #pragma unroll
         for (int r = 0; r < L; ++r) st[r] = T(0);
 #pragma unroll
@@ -303,11 +315,11 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         lds_row<T, L>(acc, N + Cf::A + r * L);
         lds_row<T, L>(st, N + Cf::C + r * L);
 #pragma unroll
-        for (int k = 0; k < L; ++k) sdcol[k] = has_odd ? N[Cf::B + k * L + r] : T(0);
+        for (int k = 0; k < L; ++k) sdcol[k] = N[Cf::B + k * L + r];
 #pragma unroll
         for (int k = 0; k < L; ++k) {
           axpy_row<T, L>(acc, -sdcol[k], P[k]);
-          axpy_row<T, L>(acc, has_left ? -st[k] : T(0), Q[k]);
+          axpy_row<T, L>(acc, -st[k], Q[k]);
         }
         if (grad) {
           T wr = T(0);

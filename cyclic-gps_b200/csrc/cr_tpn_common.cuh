@@ -37,6 +37,26 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
       constexpr int CPR = CPU * GRP;        // chunks per record (for this field group)
       const int total = nunits * CPU;
       const char* gp = reinterpret_cast<const char*>(g) + lane * 16;
+      if constexpr ((32 % CPR) == 0 || (CPR % 32) == 0) {
+        // a warp step of 32 chunks advances by a whole number of records (or stays inside one): the shared
+        // address is a plain induction variable -> 2 integer adds per 16-byte chunk
+        const unsigned k0 = (unsigned)(lane + kstart * CPU);
+        unsigned rec = k0 / CPR, c = k0 - rec * CPR;
+        unsigned saddr = srec0 + rec * nsb + c * 16;
+        if constexpr ((32 % CPR) == 0) {
+          const unsigned step = (32 / CPR) * nsb;
+          for (int i = lane; i < total; i += 32, gp += 512, saddr += step) cp_async16_u32(saddr, gp);
+        } else {
+          // CPR is a multiple of 32: stay in the record for CPR/32 steps, then jump to the next one
+          constexpr unsigned SPR = CPR / 32;
+          unsigned j = c / 32;
+          for (int i = lane; i < total; i += 32, gp += 512) {
+            cp_async16_u32(saddr, gp);
+            if (++j == SPR) { j = 0; saddr += nsb - (SPR - 1) * 512; } else { saddr += 512; }
+          }
+        }
+        return;
+      }
       for (int i = lane; i < total; i += 32, gp += 512) {
         const unsigned k = (unsigned)(i + kstart * CPU);
         const unsigned rec = k / CPR, c = k - rec * CPR;
@@ -67,6 +87,23 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
       constexpr int CPR = CPU * GRP;
       const int total = nunits * CPU;
       char* gp = reinterpret_cast<char*>(g) + lane * 16;
+      if constexpr ((32 % CPR) == 0 || (CPR % 32) == 0) {
+        const unsigned k0 = (unsigned)(lane + kstart * CPU);
+        unsigned rec = k0 / CPR, c = k0 - rec * CPR;
+        unsigned saddr = srec0 + rec * nsb + c * 16;
+        if constexpr ((32 % CPR) == 0) {
+          const unsigned step = (32 / CPR) * nsb;
+          for (int i = lane; i < total; i += 32, gp += 512, saddr += step) *reinterpret_cast<int4*>(gp) = lds128_u32(saddr);
+        } else {
+          constexpr unsigned SPR = CPR / 32;
+          unsigned j = c / 32;
+          for (int i = lane; i < total; i += 32, gp += 512) {
+            *reinterpret_cast<int4*>(gp) = lds128_u32(saddr);
+            if (++j == SPR) { j = 0; saddr += nsb - (SPR - 1) * 512; } else { saddr += 512; }
+          }
+        }
+        return;
+      }
       for (int i = lane; i < total; i += 32, gp += 512) {
         const unsigned k = (unsigned)(i + kstart * CPU);
         const unsigned rec = k / CPR, c = k - rec * CPR;
@@ -82,6 +119,21 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
     const unsigned rec = k / EPR, c = k - rec * EPR;
     g[i] = reinterpret_cast<const T*>(__cvta_shared_to_generic(srec0 + rec * nsb))[c];
   }
+}
+
+// Boundary lanes (no node, no odd neighbour, no left link) get neutral operands written into their own
+// shared-memory record once, so that the dense algebra needs no per-element selects.
+template <typename T, int N>
+__device__ __forceinline__ void smem_fill_zero(T* p) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = T(0);
+}
+template <typename T, int L>
+__device__ __forceinline__ void smem_fill_identity(T* p) {
+#pragma unroll
+  for (int r = 0; r < L; ++r)
+#pragma unroll
+    for (int c = 0; c < L; ++c) p[r * L + c] = (r == c) ? T(1) : T(0);
 }
 
 // compiler-only fence: stops the scheduler from hoisting later shared-memory loads above this

@@ -138,6 +138,9 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   const bool do_f = own && (e < o);
   const bool has_left = valid && (e >= 1 || halo);
 
+  // neutral operands for lanes without a node (R = I, y = 0), written once into the lane's own record so that
+  // the dense algebra below needs no per-element selects
+  if (!valid) { smem_fill_identity<T, L>(N + C::RE); smem_fill_zero<T, L>(N + C::YE); }
   T K[L][L];
   T inv[L];
   bool bad = false;
@@ -146,7 +149,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
     T row[L];
     lds_row<T, L>(row, N + C::RE + r * L);
 #pragma unroll
-    for (int c = 0; c < L; ++c) K[r][c] = valid ? row[c] : (r == c ? T(1) : T(0));
+    for (int c = 0; c < L; ++c) K[r][c] = row[c];
   }
   double dprod = 1.0;
 #pragma unroll
@@ -185,17 +188,13 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
 #pragma unroll
   for (int c = 0; c < L; ++c) x[c] = T(0);
   if (has_y) {
-    if (valid) lds_row<T, L>(x, N + C::YE);
+    lds_row<T, L>(x, N + C::YE);
 #pragma unroll
     for (int c = 0; c < L; ++c) {
       T s = x[c];
 #pragma unroll
       for (int k = 0; k < c; ++k) s = fma(-x[k], K[c][k], s);
       x[c] = s * inv[c];
-    }
-    if (!valid) {
-#pragma unroll
-      for (int c = 0; c < L; ++c) x[c] = T(0);
     }
     if (valid) sts_row<T, L>(N + C::YE, x);
     if (own) {
@@ -207,6 +206,9 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   out_D_x();                     // K and x leave now; the stores overlap the rest of the kernel
   cp_async_wait_group<0>();      // O tile has landed
   __syncwarp();
+  // no odd neighbour (or halo lane) -> O_right = 0 ; no left link -> O_left = 0   (boundary lanes only)
+  if (!do_f) smem_fill_zero<T, BS>(N + C::OR_);
+  if (!has_left) smem_fill_zero<T, BS>(N + C::OL);
 
   // F = O_right K^{-T} (row by row), A = F F^T (lower), u = F x
   T A[L][L];   // only r >= c used
@@ -219,7 +221,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       lds_row<T, L>(f, N + C::OR_ + r * L);
 #pragma unroll
       for (int c = 0; c < L; ++c) {
-        T s = do_f ? f[c] : T(0);
+        T s = f[c];
 #pragma unroll
         for (int k = 0; k < c; ++k) s = fma(-f[k], K[c][k], s);
         f[c] = s * inv[c];
@@ -252,7 +254,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       T row[L];
       lds_row<T, L>(row, N + C::OL + c * L);
 #pragma unroll
-      for (int r = 0; r < L; ++r) G[r][c] = has_left ? row[r] : T(0);
+      for (int r = 0; r < L; ++r) G[r][c] = row[r];
     }
 #pragma unroll
     for (int r = 0; r < L; ++r) {
@@ -328,7 +330,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
 
   // R~_e = R_odd - A - B_{e+1},  y~_e = y_odd - u - v_{e+1}
   if (do_f) {
-    const bool next_even = (e + 1) < E;
+    // (no even node e+1: the lane to the right holds G = 0, so B and v arrive as zeros)
 #pragma unroll
     for (int r = 0; r < L; ++r) {
       T row[L];
@@ -337,7 +339,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       for (int c = 0; c < L; ++c) {
         const T av = (r >= c) ? A[r][c] : A[c][r];
         const T bv = (r >= c) ? Bn[r][c] : Bn[c][r];
-        row[c] = row[c] - av - (next_even ? bv : T(0));
+        row[c] = row[c] - av - bv;
       }
       sts_row<T, L>(N + C::RO + r * L, row);
     }
@@ -345,7 +347,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
       T yo[L];
       lds_row<T, L>(yo, N + C::YO);
 #pragma unroll
-      for (int r = 0; r < L; ++r) yo[r] = yo[r] - u[r] - (next_even ? vn[r] : T(0));
+      for (int r = 0; r < L; ++r) yo[r] = yo[r] - u[r] - vn[r];
       sts_row<T, L>(N + C::YO, yo);
     }
   }
