@@ -139,6 +139,35 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
   return CRB200_OK;
 }
 
+int crb200_sweep_halfsolve(int dtype, int ell, const crb200_sweep_hs_args* a, void* stream) {
+  if (a == nullptr) return CRB200_EINVAL;
+  if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
+  if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->D == nullptr || a->y == nullptr || a->X == nullptr) return CRB200_EINVAL;
+  const int es = dtype == CRB200_F32 ? 4 : 8;
+  const long long bs = (long long)ell * ell, B = a->batch;
+  crb200_hs_args l{};
+  l.batch = a->batch; l.mahal = a->mahal;
+  l.y = a->y; l.stridey = a->stridey;
+  long long offE = 0, offO = 0, offG = 0;
+  int m = a->n;
+  for (int k = 0; k < a->nlevels; ++k) {
+    if (m < 1) return CRB200_EINVAL;
+    const long long E = (m + 1) / 2, o = m / 2, g = (m - 1) / 2;
+    l.m = m;
+    l.D = adv(a->D, B * bs * offE, es);
+    l.F = o > 0 ? adv(a->F, B * bs * offO, es) : nullptr;
+    l.G = g > 0 ? adv(a->G, B * bs * offG, es) : nullptr;
+    l.xk = adv(a->X, B * ell * offE, es);
+    l.yn = o > 0 ? a->scry[k & 1] : nullptr;
+    const int rc = crb200_level_halfsolve(dtype, ell, &l, stream);
+    if (rc != CRB200_OK) return rc;
+    l.y = l.yn; l.stridey = o * ell;
+    offE += E; offO += o; offG += g;
+    m = (int)o;
+  }
+  return CRB200_OK;
+}
+
 int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* stream) {
   if (a == nullptr) return CRB200_EINVAL;
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;

@@ -208,7 +208,7 @@ def _flat_levels(levels: Sequence[torch.Tensor]):
 
 
 def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Sequence[torch.Tensor]] = None,
-                   grad=None, top=None, halo=None, out=None):
+                   grad=None, top=None, halo=None, out=None, xs_flat: Optional[torch.Tensor] = None):
     """Deepest stored level first.  Returns (Sd, So, w) of level 0 (None for parts not asked).
 
     xs    per-level right-hand sides in CR order (default: the half-solve kept in the pack)
@@ -229,7 +229,7 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
             X_flat, X_levels = pack.X_flat, pack.X
         else:
             X_levels = [x.contiguous() for x in xs]
-            X_flat = _flat_levels(X_levels)
+            X_flat = xs_flat if xs_flat is not None else _flat_levels(X_levels)   # xs_flat: the levels already packed
     else:
         X_flat, X_levels = None, [None] * L
     D_flat = getattr(pack, "D_flat", None)
@@ -300,16 +300,30 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
 
 
 def halfsolve_sweep(pack: FactorPack, y: torch.Tensor, want_mahal: bool = False):
-    """x_k for every level against stored factors (reference halfsolve :312-338)."""
+    """x_k for every level against stored factors (reference halfsolve :312-338).  Returns (X levels, mahal)."""
     B, ell, dtype, dev = pack.batch, pack.ell, pack.dtype, y.device
+    n = pack.ms[0]
+    y = _rows_contiguous(y)
     Es = [counts(m)[0] for m in pack.ms]
-    _, X = _alloc_levels(Es, (ell,), B, dtype, dev)
+    X_flat, X = _alloc_levels(Es, (ell,), B, dtype, dev)
     acc = torch.zeros(B, dtype=torch.float64, device=dev) if want_mahal else None
-    cur, sy = y, y.stride(0)
-    for k, m in enumerate(pack.ms):
-        E, o, g = counts(m)
-        yn = torch.empty((B, o, ell), dtype=dtype, device=dev) if o > 0 else None
-        _native.level_halfsolve(dtype, ell, batch=B, m=m, D=pack.D[k], F=pack.F[k] if o > 0 else None,
-                                G=pack.G[k] if g > 0 else None, y=cur, stridey=sy, xk=X[k], yn=yn, mahal=acc)
-        cur, sy = yn, o * ell
-    return X, acc
+    if getattr(pack, "D_flat", None) is None:
+        pack.D_flat, pack.F_flat, pack.G_flat = _flat_levels(pack.D), _flat_levels(pack.F), _flat_levels(pack.G)
+    r0, r1 = n // 2, n // 4
+    scry = (torch.empty((B * r0, ell), dtype=dtype, device=dev) if r0 else None,
+            torch.empty((B * r1, ell), dtype=dtype, device=dev) if r1 else None)
+    if not _native.tracing():
+        _native.sweep_halfsolve(dtype, ell, batch=B, n=n, nlevels=pack.nlevels, D=pack.D_flat,
+                                F=pack.F_flat if (pack.F_flat is not None and pack.F_flat.numel()) else None,
+                                G=pack.G_flat if (pack.G_flat is not None and pack.G_flat.numel()) else None,
+                                y=y, stridey=y.stride(0), X=X_flat, scry=scry, mahal=acc)
+    else:
+        cur, sy = y, y.stride(0)
+        for k, m in enumerate(pack.ms):
+            E, o, g = counts(m)
+            yn = scry[k & 1] if o > 0 else None
+            _native.level_halfsolve(dtype, ell, batch=B, m=m, D=pack.D[k], F=pack.F[k] if o > 0 else None,
+                                    G=pack.G[k] if g > 0 else None, y=cur, stridey=sy, xk=X[k], yn=yn, mahal=acc)
+            cur, sy = yn, o * ell
+    pack_x = (X_flat, X)
+    return pack_x, acc

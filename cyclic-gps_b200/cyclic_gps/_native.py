@@ -72,8 +72,15 @@ class SweepBwdArgs(C.Structure):
                 ("variant", _i)]
 
 
+class SweepHsArgs(C.Structure):
+    _fields_ = [("batch", _i), ("n", _i), ("nlevels", _i),
+                ("D", _vp), ("F", _vp), ("G", _vp),
+                ("y", _vp), ("stridey", _ll),
+                ("X", _vp), ("scry", _vp * 2), ("mahal", _vp)]
+
+
 EXPORTS = ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
-           "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd",
+           "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd", "crb200_sweep_halfsolve",
            "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes")
 
 _lib = None
@@ -108,6 +115,8 @@ def load():
         lib.crb200_level_halfsolve.argtypes = [_i, _i, C.POINTER(HsArgs), _vp]
         lib.crb200_sweep_fwd.restype = _i
         lib.crb200_sweep_fwd.argtypes = [_i, _i, C.POINTER(SweepFwdArgs), _vp]
+        lib.crb200_sweep_halfsolve.restype = _i
+        lib.crb200_sweep_halfsolve.argtypes = [_i, _i, C.POINTER(SweepHsArgs), _vp]
         lib.crb200_sweep_bwd.restype = _i
         lib.crb200_sweep_bwd.argtypes = [_i, _i, C.POINTER(SweepBwdArgs), _vp]
         for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
@@ -207,6 +216,11 @@ def sweep_bwd(dtype: torch.dtype, ell: int, **fields):
     fields.setdefault("variant", VARIANT)
     a = _fill(SweepBwdArgs(), fields)
     _check(load().crb200_sweep_bwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_bwd")
+
+
+def sweep_halfsolve(dtype: torch.dtype, ell: int, **fields):
+    a = _fill(SweepHsArgs(), fields)
+    _check(load().crb200_sweep_halfsolve(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_halfsolve")
 
 
 def tracing() -> bool:

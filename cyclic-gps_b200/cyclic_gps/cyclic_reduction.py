@@ -246,7 +246,7 @@ def halfsolve(decomp, y):
     pack, batched, caller = _pack_of(decomp)
     dev = _engine.require_cuda()
     Y = _batched(_dev(y, dev, pack.dtype), batched)
-    X, _ = _engine.halfsolve_sweep(pack, Y)
+    (_, X), _ = _engine.halfsolve_sweep(pack, Y)
     return [_to_caller(x, batched, y.device) for x in X]
 
 
@@ -264,8 +264,8 @@ def solve(decomp, y):
     pack, batched, caller = _pack_of(decomp)
     dev = _engine.require_cuda()
     Y = _batched(_dev(y, dev, pack.dtype), batched)
-    X, _ = _engine.halfsolve_sweep(pack, Y)
-    _, _, w = _engine.backward_sweep(pack, sigma=False, w=True, xs=X)
+    (X_flat, X), _ = _engine.halfsolve_sweep(pack, Y)
+    _, _, w = _engine.backward_sweep(pack, sigma=False, w=True, xs=X, xs_flat=X_flat)
     return _to_caller(w, batched, y.device)
 
 

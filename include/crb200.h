@@ -128,7 +128,18 @@ typedef struct crb200_sweep_bwd_args {
   int variant;
 } crb200_sweep_bwd_args;
 
+/* All levels of halfsolve (:312-338) / mahal (:461-467) against packed factors: X receives x_k of every level
+ * (packed like D rows); scry[] ping-pong as in the forward sweep; mahal (batch doubles, NULL to skip). */
+typedef struct crb200_sweep_hs_args {
+  int batch, n, nlevels;
+  const void* D; const void* F; const void* G;
+  const void* y; long long stridey;
+  void* X; void* scry[2];
+  double* mahal;
+} crb200_sweep_hs_args;
+
 int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* args, void* stream);
+int crb200_sweep_halfsolve(int dtype, int ell, const crb200_sweep_hs_args* args, void* stream);
 int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* args, void* stream);
 
 int crb200_version(void);

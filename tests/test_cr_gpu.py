@@ -204,6 +204,41 @@ def test_every_kernel_family_vs_oracle(l, n, dtype, variant):
         assert_close(a, b, tol, f"D[{k}] (variant {variant})")
 
 
+def test_per_level_entries_equal_the_sweep_entries():
+    """libcrb200 offers the level loop inside the library (crb200_sweep_*) and one entry per level
+    (crb200_level_*, used when bench.py times every launch).  Both must give the same numbers."""
+    from cyclic_gps import _native
+
+    class Tracer:                      # any object with begin/end switches the engine to the per-level entries
+        enabled = True
+        launches = 0
+
+        def begin(self, kind, dtype, ell, batch, m):
+            Tracer.launches += 1
+            return None
+
+        def end(self, tok):
+            return None
+
+    c = cr()
+    for (l, n, dtype) in ((8, 1500, torch.float32), (3, 700, torch.float64), (16, 130, torch.float64)):
+        R, O, x = (t.cuda() for t in leg_inputs(l, n, dtype, seed=n))
+        results = []
+        for traced in (False, True):
+            _native.TRACE = Tracer() if traced else None
+            try:
+                Rr, Or, xr = [t.clone().requires_grad_(True) for t in (R, O, x)]
+                mm, dd = c.mahal_and_det(Rr, Or, xr)
+                (mm - 2 * dd).backward()
+                dec = c.decompose(R, O)
+                results.append((mm, dd, Rr.grad, Or.grad, xr.grad, c.solve(dec, x), c.mahal(dec, x), *c.inverse_blocks(dec), *c.halfsolve(dec, x)))
+            finally:
+                _native.TRACE = None
+        for a, b in zip(*results):
+            assert_close(a, b, 1e-12 if dtype == torch.float64 else 1e-5, "per-level vs sweep")
+    assert Tracer.launches > 0
+
+
 def test_det_of_decompose_is_differentiable():
     c = cr()
     R, O, _ = leg_inputs(4, 300, torch.float64, seed=5)
