@@ -19,13 +19,22 @@
 
 namespace crb200 {
 
+// record layout of the column-split kernel (five blocks; see cr_tpn_bwd.cuh for the roles)
+template <typename T, int L>
+struct CsBwdRec {
+  static constexpr int BS = L * L;
+  static constexpr int A = 0, SD = BS, C = 2 * BS, B = 3 * BS, SO = 4 * BS, X = 5 * BS, WT = 5 * BS + L;
+  static constexpr int RAW = 5 * BS + 2 * L;
+  static constexpr int NS = record_stride<T>(RAW);
+};
+
 template <typename T, int L, int LPN>
 struct CsBwdCfg {
   static constexpr int CW = L / LPN;
   static constexpr bool ELIGIBLE = (L % LPN == 0) && (LPN > 1) && (L <= 8) && ((CW * (int)sizeof(T)) % 16 == 0);
   static constexpr int BS = L * L;
   static constexpr int NT = 32 / LPN;          // nodes per warp
-  using Rec = TpnBwdCfg<T, L>;                 // same record layout
+  using Rec = CsBwdRec<T, L>;
   static constexpr int NS = Rec::NS;
   static constexpr size_t SMEM = (size_t)(NT + 1) * NS * sizeof(T);
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));

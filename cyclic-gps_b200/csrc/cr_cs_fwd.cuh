@@ -15,13 +15,22 @@
 
 namespace crb200 {
 
+// record layout of the row-split kernel: [ R_even | R_odd | O_left | O_right | O~ | y_even | y_odd ]
+template <typename T, int L>
+struct CsFwdRec {
+  static constexpr int BS = L * L;
+  static constexpr int RE = 0, RO = BS, OL = 2 * BS, OR_ = 3 * BS, ON = 4 * BS, YE = 5 * BS, YO = 5 * BS + L;
+  static constexpr int RAW = 5 * BS + 2 * L;
+  static constexpr int NS = record_stride<T>(RAW);
+};
+
 template <typename T, int L, int LPN>
 struct CsFwdCfg {
   static constexpr int RW = L / LPN;
   static constexpr bool ELIGIBLE = (L % LPN == 0) && (LPN > 1) && (L <= 8) && ((RW * (int)sizeof(T)) % 16 == 0);
   static constexpr int BS = L * L;
   static constexpr int NT = 32 / LPN, OWN = NT - 1;
-  using Rec = TpnFwdCfg<T, L>;
+  using Rec = CsFwdRec<T, L>;
   static constexpr int NS = Rec::NS;
   static constexpr size_t SMEM = (size_t)NT * NS * sizeof(T);
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));

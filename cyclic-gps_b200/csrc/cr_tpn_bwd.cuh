@@ -31,7 +31,7 @@ struct TpnBwdCfg {
   static constexpr int NS = record_stride<T>(RAW);
   static constexpr size_t SMEM_W = (size_t)(NT + 1) * NS * sizeof(T);           // per warp
   static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
-  static constexpr size_t SMEM = SMEM_W * NW;
+  static constexpr size_t SMEM = SMEM_W * NW + CRB200_SMEM_PAD;   // CRB200_SMEM_PAD: occupancy experiments only
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
 };
 

@@ -7,6 +7,9 @@
 #pragma once
 #include "cr_common.cuh"
 
+#ifndef CRB200_SMEM_PAD
+#define CRB200_SMEM_PAD 0      // extra dynamic shared memory per CTA (lowers the CTAs/SM; profiling experiments)
+#endif
 #ifndef CRB200_TPN_WARPS
 #define CRB200_TPN_WARPS 1     // independent single-tile warps per CTA of the thread-per-node kernels
 #endif
@@ -73,6 +76,59 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
     T* dst = reinterpret_cast<T*>(__cvta_shared_to_generic(srec0 + rec * nsb)) + c;
     cp_async_elem(dst, g + i);
   }
+}
+
+// Every GS-th global unit -> one unit per record (unit j = global unit j * GS lands in record kstart + j).
+// Used to stage only the even (or only the odd) rows of a level.
+template <typename T, int UE, int GS>
+__device__ __forceinline__ void rec_g2s_strided(unsigned srec0, unsigned nsb, const T* __restrict__ g, int kstart, int nunits, bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if (nunits <= 0) return;
+  const int lane = threadIdx.x & 31;
+  if constexpr ((UE % VE) == 0) {
+    if (vec_ok) {
+      constexpr int CPU = UE / VE;
+      const int total = nunits * CPU;
+      if constexpr ((32 % CPU) == 0) {
+        const unsigned j0 = (unsigned)lane / CPU, c = (unsigned)lane - j0 * CPU;
+        unsigned saddr = srec0 + (kstart + j0) * nsb + c * 16;
+        const char* gp = reinterpret_cast<const char*>(g) + ((size_t)j0 * GS * CPU + c) * 16;
+        const unsigned sstep = (32 / CPU) * nsb;
+        constexpr size_t gstep = (size_t)(32 / CPU) * GS * CPU * 16;
+        for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) cp_async16_u32(saddr, gp);
+        return;
+      }
+      for (int i = lane; i < total; i += 32) {
+        const unsigned j = (unsigned)i / CPU, c = (unsigned)i - j * CPU;
+        cp_async16_u32(srec0 + (kstart + j) * nsb + c * 16, reinterpret_cast<const char*>(g) + ((size_t)j * GS * CPU + c) * 16);
+      }
+      return;
+    }
+  }
+  const int total = nunits * UE;
+  for (int i = lane; i < total; i += 32) {
+    const unsigned j = (unsigned)i / UE, c = (unsigned)i - j * UE;
+    T* dst = reinterpret_cast<T*>(__cvta_shared_to_generic(srec0 + (kstart + j) * nsb)) + c;
+    cp_async_elem(dst, g + (size_t)j * GS * UE + c);
+  }
+}
+
+// one row of L elements from registers straight to global memory (16-byte stores when aligned)
+template <typename T, int L>
+__device__ __forceinline__ void stg_row(T* p, const T (&a)[L], bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if constexpr ((L % VE) == 0) {
+    if (vec_ok) {
+#pragma unroll
+      for (int c = 0; c < L; c += VE) {
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(p + c) = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
+        else *reinterpret_cast<double2*>(p + c) = make_double2(a[c], a[c + 1]);
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < L; ++c) p[c] = a[c];
 }
 
 // Records -> global units, same addressing.

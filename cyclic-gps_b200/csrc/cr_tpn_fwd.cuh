@@ -10,10 +10,14 @@
 // overlap each other's load / compute / store phases.
 //
 // Shared memory holds one padded record per node,
-//     [ R_even | R_odd | O_left | O_right | O~ | y_even | y_odd ]   (stride NS, NS/16B odd)
-// filled by cp.async from three flat coalesced global ranges; results are written in place
-// (R_even->K, R_odd->R~, O_left->G, O_right->F, y_even->x, y_odd->y~) and leave as flat
-// coalesced ranges.  The odd record stride makes the per-thread 16-byte accesses conflict free.
+//     [ R | O_left | O_right | y_even | y_odd ]   (stride NS, NS/16B odd, 848 B at ell = 8 fp32)
+// filled by cp.async from coalesced global ranges; results are written in place (R_even->K, O_left->G,
+// O_right->F, y_even->x, y_odd->y~) and leave as flat coalesced ranges.  The R slot is used TWICE: it
+// first holds R_even (-> K, copied out as soon as it exists), then R_odd is staged into it while F and G
+// are being computed, and R~ is finished there.  O~ rows go from registers straight to global memory.
+// Three blocks per node instead of five means 8 resident CTAs per SM instead of 5; measured throughput of
+// this kernel scales almost linearly with resident CTAs (profiles/r1_summary.md).
+// The odd record stride makes the per-thread 16-byte accesses conflict free.
 #pragma once
 #include "cr_common.cuh"
 #include "cr_level_fwd.cuh"
@@ -26,13 +30,13 @@ struct TpnFwdCfg {
   static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= 256);
   static constexpr int BS = L * L;
   static constexpr int NT = 32, OWN = 31;
-  static constexpr int RE = 0, RO = BS, OL = 2 * BS, OR_ = 3 * BS, ON = 4 * BS, YE = 5 * BS, YO = 5 * BS + L;
-  static constexpr int RAW = 5 * BS + 2 * L;
+  static constexpr int RE = 0, OL = BS, OR_ = 2 * BS, YE = 3 * BS, YO = 3 * BS + L;   // RE: R_even, later R_odd -> R~
+  static constexpr int RAW = 3 * BS + 2 * L;
   static constexpr int NS = record_stride<T>(RAW);
   static constexpr size_t SMEM_W = (size_t)NT * NS * sizeof(T);                 // per warp
   // independent warps per CTA (each warp = one tile): warps of a CTA run the same code at about the same time
   static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
-  static constexpr size_t SMEM = SMEM_W * NW;
+  static constexpr size_t SMEM = SMEM_W * NW + CRB200_SMEM_PAD;   // CRB200_SMEM_PAD: occupancy experiments only
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((224 * 1024) / (SMEM + 1024))));
 };
 
@@ -71,7 +75,7 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
-    rec_g2s<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, nR, is_aligned16(gR));
+    rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, (nR + 1) >> 1, is_aligned16(gR));   // even rows
     if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
     cp_async_commit();
     const int pfirst = (r0 == 0) ? 1 : 0;
@@ -106,17 +110,17 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   };
   auto out_reduced = [&]() {
     if (a.Rn != nullptr && n_odd > 0) {
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RO * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+      rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
       if (has_y && a.yn != nullptr)
         rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
-      const int ofirst = (e0 == 0) ? 1 : 0;
-      const int n_on = cmax(0, cmin(e0 + n_own, o) - (e0 + ofirst));
-      if (a.On != nullptr && n_on > 0)
-        rec_s2g<T, BS, 1>(static_cast<T*>(a.On) + ((size_t)b * (o - 1) + (e0 + ofirst - 1)) * BS, s0 + C::ON * ES, nsb, ofirst, n_on,
-                          is_aligned16(a.On));
     }
-    if (halo && e0 == 0 && a.On_halo != nullptr && o > 0)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.On_halo) + (size_t)b * BS, s0 + C::ON * ES, nsb, 0, 1, is_aligned16(a.On_halo));
+  };
+  // R_odd of this tile -> the R slot (second use), issued once K has been copied out
+  auto stage_R_odd = [&]() {
+    const int r0 = 2 * e0;
+    const int nR = cmin(2 * NT - 1, m - r0);
+    rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * BS, 0, nR >> 1, is_aligned16(gR));
+    cp_async_commit();
   };
 
   // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
@@ -124,7 +128,18 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   if (a.variant == CRB200_COPY_ONLY) {
     cp_async_wait_group<0>();
     __syncwarp();
-    out_D_x(); out_F(); out_G(); out_reduced();
+    out_D_x(); out_F(); out_G();
+    __syncwarp();
+    stage_R_odd();
+    cp_async_wait_group<0>();
+    __syncwarp();
+    out_reduced();
+    if (a.On != nullptr && n_odd > 1 && lane < n_odd - 1)      // same bytes as the real kernel's direct O~ stores
+      for (int r = 0; r < L; ++r) {
+        T z[L];
+        lds_row<T, L>(z, S + (size_t)lane * NS + C::OL + r * L);
+        stg_row<T, L>(static_cast<T*>(a.On) + ((size_t)b * (o - 1) + e0 + lane) * BS + r * L, z, is_aligned16(a.On));
+      }
     return;
   }
   {
@@ -204,7 +219,9 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   }
   __syncwarp();
   out_D_x();                     // K and x leave now; the stores overlap the rest of the kernel
+  __syncwarp();                  // the R slot has been read out by every lane
   cp_async_wait_group<0>();      // O tile has landed
+  stage_R_odd();                 // R_odd -> R slot, arrives while F and G are computed
   __syncwarp();
   // no odd neighbour (or halo lane) -> O_right = 0 ; no left link -> O_left = 0   (boundary lanes only)
   if (!do_f) smem_fill_zero<T, BS>(N + C::OR_);
@@ -287,7 +304,12 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
         for (int k = 0; k < L; ++k) s = fma(-f[k], G[c][k], s);
         on[c] = s;
       }
-      sts_row<T, L>(N + C::ON + r * L, on);
+      // O~_{e-1}[r,:] straight to global memory (one 32-byte sector per row at ell = 8 fp32)
+      T* base = static_cast<T*>(e >= 1 ? a.On : a.On_halo);
+      if (base != nullptr) {
+        T* dst = base + ((e >= 1) ? ((size_t)b * (o - 1) + (e - 1)) * BS : (size_t)b * BS);
+        stg_row<T, L>(dst + r * L, on, is_aligned16(base));
+      }
     }
   }
   T Bn[L][L];   // lower: G G^T of the NEXT even node after the shuffle
@@ -329,19 +351,21 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
   }
 
   // R~_e = R_odd - A - B_{e+1},  y~_e = y_odd - u - v_{e+1}
+  cp_async_wait_group<0>();      // R_odd has landed in the R slot
+  __syncwarp();
   if (do_f) {
     // (no even node e+1: the lane to the right holds G = 0, so B and v arrive as zeros)
 #pragma unroll
     for (int r = 0; r < L; ++r) {
       T row[L];
-      lds_row<T, L>(row, N + C::RO + r * L);
+      lds_row<T, L>(row, N + C::RE + r * L);
 #pragma unroll
       for (int c = 0; c < L; ++c) {
         const T av = (r >= c) ? A[r][c] : A[c][r];
         const T bv = (r >= c) ? Bn[r][c] : Bn[c][r];
         row[c] = row[c] - av - bv;
       }
-      sts_row<T, L>(N + C::RO + r * L, row);
+      sts_row<T, L>(N + C::RE + r * L, row);
     }
     if (has_y) {
       T yo[L];
