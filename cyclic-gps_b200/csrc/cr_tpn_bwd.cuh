@@ -2,19 +2,26 @@
 //
 // Same contract as cr_level_bwd_kernel (cr_level_bwd.cuh: back-half-solve + selected inverse +
 // optional gradient assembly; reference cyclic_gps/cyclic_reduction.py:362-373, :478-501),
-// different mapping: ONE THREAD owns one even node e and keeps P = F D^{-1} and Q = G D^{-1}
-// in registers for the whole kernel; every other operand is streamed row by row from the
-// thread's own shared-memory record with conflict-free 16-byte accesses.  A CTA is one warp
-// (32 even nodes); the only data shared between threads are S~_d[e-1] and w~_{e-1}, read from
-// the left neighbour's record.
+// different mapping: ONE THREAD owns one even node e and keeps P = F D^{-1}, Q = G D^{-1} and the
+// lower triangle of Sigma_{2e,2e} in registers for the whole kernel; every other operand is streamed
+// row by row from the thread's own shared-memory record with conflict-free 16-byte accesses.  A CTA
+// is one warp (32 even nodes); the only data shared between threads are S~_d[e-1] and w~_{e-1}, read
+// from the left neighbour's record.
 //
-// Record layout (stride NS, NS/16 B odd), with the fields that leave as interleaved rows kept
-// adjacent so that the interleave (reference interleave(), :181-200) is a plain pair copy:
-//   [ A : D_e      -> Sigma_{2e,2e}   | SD : S~_d[e] (Sigma_{2e+1,2e+1})        ]  -> Sd_out rows 2e, 2e+1
-//   [ C : G_{e-1}  -> Sigma_{2e,2e-1} | B  : F_e -> Sigma_{2e+1,2e}             ]  -> So_out rows 2e-1, 2e
-//   [ SO: S~_o[e-1] (input only) ]
-//   [ X : x_e -> w_{2e}               | WT : w~_e (w_{2e+1})                    ]  -> w_out rows 2e, 2e+1
-// Record 0 is the left neighbour (deeper-level node e0-1) and only carries SD and WT.
+// COMPACT record layout (stride NS, NS/16 B odd; 848 B at ell = 8 fp32), THREE blocks per node, each used twice
+// (chosen when five blocks per node would leave fewer than 8 CTAs per SM: fp32 ell = 7, 8 and fp64 ell = 5):
+//   [ A : D_e, then S~_d[e] (= Sigma_{2e+1,2e+1})                 ]  -> Sd_out row 2e+1
+//   [ C : G_{e-1}        -> Sigma_{2e,2e-1} | B : F_e, then S~_o[e-1] -> Sigma_{2e+1,2e} ]  -> So_out rows 2e-1, 2e
+//   [ X : x_e -> w_{2e}                     | WT : w~_e (w_{2e+1})    ]  -> w_out rows 2e, 2e+1
+// D is turned into D^{-1} in registers at once and S~_d is staged over it; F is consumed into P and S~_o
+// is staged over it; both arrive while P, Q and w are being computed.  Sigma_{2e,2e} never touches shared
+// memory: it starts as D^{-T} D^{-1} in registers, is finished from the rows of Sigma_{2e+1,2e} and
+// Sigma_{2e,2e-1}, and its rows go from registers straight to global memory.  Three blocks instead of five
+// per node means 8 resident single-warp CTAs per SM instead of 5, which is what this latency-bound kernel
+// needs: 2.71 -> 2.18 ms for the level-0 launch of configs[1] (profiles/r1_summary.md).
+// Small blocks keep FIVE blocks per node, [ A | SD | C | B | SO | X | WT ]: everything is requested up front,
+// Sigma_{2e,2e} is written into A, and (A, SD), (C, B), (X, WT) leave as interleaved pairs.
+// Record 0 is the left neighbour (deeper-level node e0-1) and only carries S~_d and WT.
 #pragma once
 #include "cr_level_bwd.cuh"
 #include "cr_tpn_common.cuh"
@@ -26,13 +33,20 @@ struct TpnBwdCfg {
   static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= 256);
   static constexpr int BS = L * L;
   static constexpr int NT = 32;
-  static constexpr int A = 0, SD = BS, C = 2 * BS, B = 3 * BS, SO = 4 * BS, X = 5 * BS, WT = 5 * BS + L;
-  static constexpr int RAW = 5 * BS + 2 * L;
+  // COMPACT (three blocks per node, A and B slots used twice) when five blocks per node would leave fewer than
+  // 8 CTAs on an SM (fp32 ell = 7, 8; fp64 ell = 5); otherwise S~_d and S~_o get slots of their own, everything is
+  // requested up front and Sigma_{2e,2e} leaves through the A slot (measured: at ell = 4 fp32, 17 CTAs/SM with five
+  // blocks beat 26 CTAs/SM with three blocks and three dependent load phases, 5.34 vs 6.03 ms on the long series)
+  static constexpr int CTAS5 = (int)((228 * 1024) / ((size_t)(NT + 1) * record_stride<T>(5 * BS + 2 * L) * sizeof(T) + 1024));
+  static constexpr bool COMPACT = CTAS5 < 8;
+  static constexpr int A = 0, SD = COMPACT ? 0 : BS, C = COMPACT ? BS : 2 * BS, B = C + BS, SO = COMPACT ? B : 4 * BS;
+  static constexpr int X = (COMPACT ? 3 : 5) * BS, WT = X + L;
+  static constexpr int RAW = X + 2 * L;
   static constexpr int NS = record_stride<T>(RAW);
   static constexpr size_t SMEM_W = (size_t)(NT + 1) * NS * sizeof(T);           // per warp
   static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
   static constexpr size_t SMEM = SMEM_W * NW + CRB200_SMEM_PAD;   // CRB200_SMEM_PAD: occupancy experiments only
-  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
+  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((228 * 1024) / (SMEM + 1024))));
 };
 
 
@@ -62,21 +76,19 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   const bool do_w = a.w_out != nullptr;
   const bool halo = a.G_halo != nullptr;
   const int lane = threadIdx.x & 31;
+  const int nF = cmax(0, cmin(NT, o - e0));                      // odd neighbours e0 .. of this tile
+  const int ilo = (e0 == 0) ? 1 : 0;
+  const int nodd = cmin(e0 + NT, o) - (e0 - 1 + ilo);            // deeper node e0-1+i -> record i
 
-  // ---------------- stage in: two cp.async groups ----------------
-  // group 0 = factors D, F, G and the vectors (needed first: D^{-1}, P, Q, w); group 1 = S~_d, S~_o of the
-  // deeper level.  The triangular inverse and the P / Q products overlap the arrival of group 1.
+  // ---------------- stage in, first group: factors D, F, G and the vectors ----------------
   {
     rec_g2s<T, BS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * BS, 0, nE, is_aligned16(a.D));
-    const int nF = cmax(0, cmin(NT, o - e0));
     rec_g2s<T, BS, 1>(rec1 + Cf::B * ES, nsb, static_cast<const T*>(a.F) + ((size_t)b * o + e0) * BS, 0, nF, is_aligned16(a.F));
     const int gf = (e0 == 0) ? 1 : 0;
     rec_g2s<T, BS, 1>(rec1 + Cf::C * ES, nsb, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e0 + gf - 1)) * BS, gf, nE - gf,
                       is_aligned16(a.G));
     if (e0 == 0 && halo)
       rec_g2s<T, BS, 1>(rec1 + Cf::C * ES, nsb, static_cast<const T*>(a.G_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.G_halo));
-    const int ilo = (e0 == 0) ? 1 : 0;
-    const int nodd = cmin(e0 + NT, o) - (e0 - 1 + ilo);          // deeper node e0-1+i -> record i
     if (do_w) {
       rec_g2s<T, L, 1>(rec1 + Cf::X * ES, nsb, static_cast<const T*>(a.xk) + ((size_t)b * E + e0) * L, 0, nE, is_aligned16(a.xk));
       rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_in) + ((size_t)b * o + (e0 - 1 + ilo)) * L, ilo, nodd,
@@ -85,32 +97,42 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         rec_g2s<T, L, 1>(s0 + Cf::WT * ES, nsb, static_cast<const T*>(a.w_halo) + (size_t)b * L, 0, 1, is_aligned16(a.w_halo));
     }
     cp_async_commit();
+  }
+  // S~_d of the deeper level (record i <- deeper node e0-1+i); COMPACT: second use of the A slots
+  auto stage_Sd = [&]() {
     if (do_sigma) {
       rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * BS, ilo, nodd,
                         is_aligned16(a.Sd_in));
-      const int nso = cmin(e0 + NT - 1, o - 1) - (e0 - 1 + ilo);  // link e0-1+i -> record i+1
-      rec_g2s<T, BS, 1>(rec1 + Cf::SO * ES, nsb, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e0 - 1 + ilo)) * BS, ilo, nso,
-                        is_aligned16(a.So_in));
-      if (e0 == 0 && halo) {
+      if (e0 == 0 && halo)
         rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.Sd_halo));
-        if (o > 0)
-          rec_g2s<T, BS, 1>(rec1 + Cf::SO * ES, nsb, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, 0, 1, is_aligned16(a.So_halo_in));
-      }
     }
     cp_async_commit();
-    cp_async_wait_group<1>();      // factors and vectors have landed
-    __syncwarp();
-  }
+  };
+  // S~_o of the deeper level (link e0-1+i -> record i+1); COMPACT: second use of the B slots
+  auto stage_So = [&]() {
+    if (do_sigma) {
+      const int nso = cmin(e0 + NT - 1, o - 1) - (e0 - 1 + ilo);
+      rec_g2s<T, BS, 1>(rec1 + Cf::SO * ES, nsb, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e0 - 1 + ilo)) * BS, ilo, nso,
+                        is_aligned16(a.So_in));
+      if (e0 == 0 && halo && o > 0)
+        rec_g2s<T, BS, 1>(rec1 + Cf::SO * ES, nsb, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, 0, 1, is_aligned16(a.So_halo_in));
+    }
+    cp_async_commit();
+  };
 
   // ---------------- stage out, piece by piece ----------------
   const int row_lo = 2 * e0;
   const int nrows = cmin(2 * nE, m - row_lo);
   const int so_plo = (e0 == 0) ? 1 : 0;
   const int nso_rows = cmin(2 * e0 + 2 * nE - 1, m - 1) - (2 * e0 - 1 + so_plo);
+  T* const gSd = do_sigma ? static_cast<T*>(a.Sd_out) + (size_t)b * a.strideSd : nullptr;
+  const bool sd_vec = is_aligned16(gSd);
   auto out_Sd = [&]() {
     if (do_sigma) {
-      T* Sd = static_cast<T*>(a.Sd_out) + (size_t)b * a.strideSd;
-      rec_s2g<T, BS, 2>(Sd + (size_t)row_lo * BS, rec1 + Cf::A * ES, nsb, 0, nrows, is_aligned16(Sd));
+      if constexpr (Cf::COMPACT)   // Sigma_{2e+1,2e+1} only (record i+1 -> Sd_out row 2(e0+i)+1); the even rows left from registers
+        rec_s2g_strided<T, BS, 2>(gSd + (size_t)(row_lo + 1) * BS, rec1 + Cf::SD * ES, nsb, 0, nF, sd_vec);
+      else                         // A and SD are adjacent: rows 2e, 2e+1 leave as pairs
+        rec_s2g<T, BS, 2>(gSd + (size_t)row_lo * BS, rec1 + Cf::A * ES, nsb, 0, nrows, sd_vec);
     }
   };
   auto out_So = [&]() {
@@ -129,25 +151,53 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
       rec_s2g<T, L, 2>(W + (size_t)row_lo * L, rec1 + Cf::X * ES, nsb, 0, nrows, is_aligned16(W));
     }
   };
-  const bool early = (a.grad_mode == 0) && (a.variant != CRB200_COPY_ONLY);   // inner levels: results are final as produced
 
-  // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
-  // ceiling of this access pattern
-  if (a.variant != CRB200_COPY_ONLY) {
-  // ---------------- per-node compute ----------------
   T* N = S + (size_t)(lane + 1) * NS;     // this node's record
   const T* Lf = S + (size_t)lane * NS;    // left neighbour's record (S~_d[e-1], w~_{e-1})
   const int e = e0 + lane;
   const bool valid = e < E;
+
+  // variant CRB200_COPY_ONLY (profiling aid): stage in, stage out, no arithmetic -> the memory-system
+  // ceiling of this access pattern (same bytes, same two uses of the A and B slots)
+  if (a.variant == CRB200_COPY_ONLY) {
+    if constexpr (Cf::COMPACT) {
+      cp_async_wait_group<0>();
+      __syncwarp();
+      if (do_sigma && valid)
+        for (int r = 0; r < L; ++r) {
+          T z[L];
+          lds_row<T, L>(z, N + Cf::A + r * L);
+          stg_row<T, L>(gSd + (size_t)(2 * e) * BS + r * L, z, sd_vec);
+        }
+      __syncwarp();
+    }
+    stage_Sd();
+    stage_So();
+    cp_async_wait_group<0>();
+    __syncwarp();
+    out_Sd(); out_So(); out_w();
+    return;
+  }
+
+  // ---------------- per-node compute ----------------
   const bool has_odd = valid && (e < o);
   const bool has_left = valid && (e >= 1 || halo);
   const bool has_so = has_left && has_odd;
   const bool grad = a.grad_mode != 0;
+  const bool early = !grad;               // inner levels: results are final as produced
   T gm = T(0), gd = T(1);
   if (grad) {
     gm = (T)(a.gm != nullptr ? a.gm[b] : 0.0);
     gd = (T)(a.gd != nullptr ? a.gd[b] : 0.0);
   }
+  if constexpr (Cf::COMPACT) {
+    cp_async_wait_group<0>();      // factors and vectors have landed
+  } else {
+    stage_Sd();                    // own slots: S~_d, S~_o are requested now and arrive during D^{-1}, P, Q
+    stage_So();
+    cp_async_wait_group<2>();      // factors and vectors have landed
+  }
+  __syncwarp();
 
   // neutral operands for boundary lanes (rare, hence divergent code is fine): no node -> D = I; no odd
   // neighbour -> F = 0, w~_e = 0; no left link -> G = 0 (and the never-loaded left record is cleared)
@@ -159,38 +209,39 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   __syncwarp();
 
   T P[L][L], Q[L][L];
+  T Mx[L][L];   // Di = D^{-1} (lower triangular), later the lower triangle of Sigma_{2e,2e}; only r >= c is used
   T dxs[L];
   {
-    // Di = D^{-1} (lower triangular), in registers
-    T Di[L][L];
 #pragma unroll
     for (int r = 0; r < L; ++r) {
       T row[L];
       lds_row<T, L>(row, N + Cf::A + r * L);
 #pragma unroll
-      for (int c = 0; c < L; ++c) Di[r][c] = row[c];   // holds K for now
+      for (int c = 0; c < L; ++c) Mx[r][c] = row[c];   // holds K for now
+    }
+    if constexpr (Cf::COMPACT) {
+      __syncwarp();                // every lane has its D in registers: the A slots are free
+      stage_Sd();                  // S~_d arrives while D^{-1}, P and Q are computed
     }
     T dinv[L];
 #pragma unroll
-    for (int c = 0; c < L; ++c) dinv[c] = T(1) / Di[c][c];
+    for (int c = 0; c < L; ++c) dinv[c] = T(1) / Mx[c][c];
 #pragma unroll
     for (int c = 0; c < L; ++c) {
-      // column c of the inverse, top to bottom; K[r][k] for k >= c is still intact in Di[r][k]
-      // only for k > c, so keep the column being replaced in a temporary
+      // column c of the inverse, top to bottom; the recurrence for column c reads K[r][k] with k >= c only,
+      // and column c is replaced after its own recurrence, so later columns still see K where they need it
       T col[L];
       col[c] = dinv[c];
 #pragma unroll
       for (int r = c + 1; r < L; ++r) {
         T s = T(0);
 #pragma unroll
-        for (int k = c; k < r; ++k) s = fma(Di[r][k], col[k], s);
+        for (int k = c; k < r; ++k) s = fma(Mx[r][k], col[k], s);
         col[r] = -s * dinv[r];
       }
 #pragma unroll
-      for (int r = c; r < L; ++r) Di[r][c] = col[r];
+      for (int r = c; r < L; ++r) Mx[r][c] = col[r];
     }
-    // note: column c of K is overwritten only after every later column's recurrence no longer needs it:
-    // the recurrence for column c' > c reads K[r][k] with k >= c' > c.
 #pragma unroll
     for (int c = 0; c < L; ++c) dxs[c] = T(0);
     if (do_w) {
@@ -200,45 +251,59 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
       for (int c = 0; c < L; ++c) {
         T s = T(0);
 #pragma unroll
-        for (int k = c; k < L; ++k) s = fma(Di[k][c], xs[k], s);
+        for (int k = c; k < L; ++k) s = fma(Mx[k][c], xs[k], s);
         dxs[c] = s;
       }
     }
-    if (do_sigma && valid) {
-#pragma unroll
-      for (int r = 0; r < L; ++r) {
-        T row[L];
-#pragma unroll
-        for (int c = 0; c < L; ++c) {
-          T s = T(0);
-#pragma unroll
-          for (int k = (r > c ? r : c); k < L; ++k) s = fma(Di[k][r], Di[k][c], s);
-          row[c] = s;
-        }
-        sts_row<T, L>(N + Cf::A + r * L, row);    // Di^T Di, the start of Sigma_{2e,2e}
-      }
-      sched_fence();
-    }
+    // P = F Di
 #pragma unroll
     for (int r = 0; r < L; ++r) {
-      T f[L], g[L];
+      T f[L];
       lds_row<T, L>(f, N + Cf::B + r * L);
+#pragma unroll
+      for (int c = 0; c < L; ++c) {
+        T sp = T(0);
+#pragma unroll
+        for (int k = c; k < L; ++k) sp = fma(f[k], Mx[k][c], sp);
+        P[r][c] = sp;
+      }
+    }
+    if constexpr (Cf::COMPACT) {
+      __syncwarp();                // every lane has consumed its F: the B slots are free
+      stage_So();                  // S~_o arrives while Q and w are computed
+    }
+    // Q = G Di
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T g[L];
       lds_row<T, L>(g, N + Cf::C + r * L);
 #pragma unroll
       for (int c = 0; c < L; ++c) {
-        T sp = T(0), sq = T(0);
+        T sq = T(0);
 #pragma unroll
-        for (int k = c; k < L; ++k) { sp = fma(f[k], Di[k][c], sp); sq = fma(g[k], Di[k][c], sq); }
-        P[r][c] = sp;
+        for (int k = c; k < L; ++k) sq = fma(g[k], Mx[k][c], sq);
         Q[r][c] = sq;
       }
-      sched_fence();
     }
+    // Di -> lower triangle of Di^T Di, in place: entry (r, c) needs Di[k][r], Di[k][c] for k >= r only, and
+    // within row r the entries are replaced left to right with (r, r) last
+#pragma unroll
+    for (int r = 0; r < L; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) {
+        T s = T(0);
+#pragma unroll
+        for (int k = r; k < L; ++k) s = fma(Mx[k][r], Mx[k][c], s);
+        Mx[r][c] = s;
+      }
   }
 
-  // w_{2e} = Di^T x_e - P^T w~_e - Q^T w~_{e-1}; parked in X (x_e is consumed) and re-read when needed
+  // w_{2e} = Di^T x_e - P^T w~_e - Q^T w~_{e-1}; kept in registers and parked in X (x_e is consumed)
+  T wv[L];
+#pragma unroll
+  for (int c = 0; c < L; ++c) wv[c] = T(0);
   if (do_w) {
-    T we[L], wl[L], wv[L];
+    T we[L], wl[L];
     lds_row<T, L>(we, N + Cf::WT);
     lds_row<T, L>(wl, Lf + Cf::WT);
 #pragma unroll
@@ -257,28 +322,12 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
     if (!has_so) smem_fill_zero<T, BS>(N + Cf::SO);
     if (lane == 0 && e0 == 0 && !halo) smem_fill_zero<T, BS>(S + Cf::SD);
     __syncwarp();
-    // The three big products run as ROLLED loops over a row / column index that only addresses
-    // shared memory (P and Q keep static register indices): 8x less code than full unrolling, which
-    // matters because five single-warp CTAs at different program counters share one SM's i-cache.
-    // Sigma_{2e+1,2e} = -(S~_d[e] P + S~_o[e-1] Q), row by row into B
-    if (has_odd) {
-#pragma unroll 1
-      for (int r = 0; r < L; ++r) {
-        T sig[L], so[L], out[L];
-        lds_row<T, L>(sig, N + Cf::SD + r * L);
-        lds_row<T, L>(so, N + Cf::SO + r * L);
-#pragma unroll
-        for (int c = 0; c < L; ++c) out[c] = T(0);
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-          axpy_row<T, L>(out, -sig[k], P[k]);
-          axpy_row<T, L>(out, -so[k], Q[k]);
-        }
-        sts_row<T, L>(N + Cf::B + r * L, out);
-      }
-    }
-    // Sigma_{2e,2e-1} = -(Q^T S~_d[e-1]^T + P^T S~_o[e-1]), COLUMN by column into C:
-    // column c needs row c of S~_d[e-1] (left record) and column c of S~_o[e-1]
+    // The two big products run as ROLLED loops over a row / column index that only addresses shared
+    // memory (P and Q keep static register indices): 8x less code than full unrolling, which matters
+    // because the single-warp CTAs of an SM sit at different program counters and share its instruction
+    // caches (fully unrolled, this kernel stalled 1.3 cycles per instruction on instruction fetch).
+    // Sigma_{2e,2e-1} = -(Q^T S~_d[e-1]^T + P^T S~_o[e-1]), COLUMN by column into C: column c needs row c of
+    // S~_d[e-1] (left record) and column c of S~_o[e-1].  (This product goes first: the next one overwrites S~_o.)
     if (has_left) {
 #pragma unroll 1
       for (int c = 0; c < L; ++c) {
@@ -297,54 +346,81 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
         for (int r = 0; r < L; ++r) N[Cf::C + r * L + c] = st[r];
       }
     }
+    // Sigma_{2e+1,2e} = -(S~_d[e] P + S~_o[e-1] Q), row by row in place over S~_o
+    if (has_odd) {
+#pragma unroll 1
+      for (int r = 0; r < L; ++r) {
+        T sig[L], so[L], out[L];
+        lds_row<T, L>(sig, N + Cf::SD + r * L);
+        lds_row<T, L>(so, N + Cf::SO + r * L);
+#pragma unroll
+        for (int c = 0; c < L; ++c) out[c] = T(0);
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+          axpy_row<T, L>(out, -sig[k], P[k]);
+          axpy_row<T, L>(out, -so[k], Q[k]);
+        }
+        sts_row<T, L>(N + Cf::B + r * L, out);
+      }
+    }
     if (early) {
       __syncwarp();
       out_So();                    // Sigma_off rows and w are final: let them leave while Sigma_{2e,2e} is computed
       out_w();
     }
-    // Sigma_{2e,2e} = Di^T Di - S_d^T P - (S_o^T) Q, row by row in place in A:
-    // row r needs column r of S_d (B) and row r of Sigma_{2e,2e-1} (C)
+    // Sigma_{2e,2e} = Di^T Di - Sigma_{2e+1,2e}^T P - Sigma_{2e,2e-1} Q: lower triangle only (it is symmetric),
+    // accumulated in the registers that hold Di^T Di; operands are rows of B and C.  Unrolled: the
+    // accumulators need static indices.  Rows then go from registers straight to global memory
+    // (gR_{2e} = gd Sigma - gm w w^T at the top level).
     if (valid) {
-      T wv[L];
 #pragma unroll
-      for (int c = 0; c < L; ++c) wv[c] = T(0);
-      if (grad && do_w) lds_row<T, L>(wv, N + Cf::X);
-#pragma unroll 1
+      for (int k = 0; k < L; ++k) {
+        T bk[L];
+        lds_row<T, L>(bk, N + Cf::B + k * L);
+#pragma unroll
+        for (int r = 0; r < L; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) Mx[r][c] = fma(-bk[r], P[k][c], Mx[r][c]);
+      }
+      T* dst = gSd + (size_t)(2 * e) * BS;
+#pragma unroll
       for (int r = 0; r < L; ++r) {
-        T acc[L], sdcol[L], st[L];
-        lds_row<T, L>(acc, N + Cf::A + r * L);
-        lds_row<T, L>(st, N + Cf::C + r * L);
+        T cr[L];
+        lds_row<T, L>(cr, N + Cf::C + r * L);
 #pragma unroll
-        for (int k = 0; k < L; ++k) sdcol[k] = N[Cf::B + k * L + r];
+        for (int c = 0; c <= r; ++c) {
+          T s = Mx[r][c];
 #pragma unroll
-        for (int k = 0; k < L; ++k) {
-          axpy_row<T, L>(acc, -sdcol[k], P[k]);
-          axpy_row<T, L>(acc, -st[k], Q[k]);
+          for (int k = 0; k < L; ++k) s = fma(-cr[k], Q[k][c], s);
+          Mx[r][c] = s;
         }
+      }
+#pragma unroll
+      for (int r = 0; r < L; ++r) {
+        T row[L];
+#pragma unroll
+        for (int c = 0; c < L; ++c) row[c] = (c <= r) ? Mx[r][c] : Mx[c][r];
         if (grad) {
-          T wr = T(0);
 #pragma unroll
-          for (int c = 0; c < L; ++c) wr = (c == r) ? wv[c] : wr;
-#pragma unroll
-          for (int c = 0; c < L; ++c) acc[c] = gd * acc[c] - gm * wr * wv[c];
+          for (int c = 0; c < L; ++c) row[c] = gd * row[c] - gm * wv[r] * wv[c];
         }
-        sts_row<T, L>(N + Cf::A + r * L, acc);
+        if constexpr (Cf::COMPACT) stg_row<T, L>(dst + r * L, row, sd_vec);
+        else sts_row<T, L>(N + Cf::A + r * L, row);
       }
     }
   }
-  __syncwarp();   // neighbours are done reading this record's SD / WT
+  __syncwarp();   // neighbours are done reading this record's S~_d / WT
 
   if (grad) {
-    T wv[L], we[L], wl[L];
+    T we[L], wl[L];
 #pragma unroll
-    for (int c = 0; c < L; ++c) { wv[c] = T(0); we[c] = T(0); wl[c] = T(0); }
+    for (int c = 0; c < L; ++c) { we[c] = T(0); wl[c] = T(0); }
     if (do_w) {
-      if (valid) lds_row<T, L>(wv, N + Cf::X);
       if (has_odd) lds_row<T, L>(we, N + Cf::WT);
       if (has_left) lds_row<T, L>(wl, Lf + Cf::WT);
     }
     if (do_sigma) {
-      if (has_odd) {
+      if (has_odd) {               // gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T ; gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T)
 #pragma unroll
         for (int r = 0; r < L; ++r) {
           T v[L];
@@ -358,7 +434,7 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
           sts_row<T, L>(N + Cf::B + r * L, v);
         }
       }
-      if (has_left) {
+      if (has_left) {              // gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)
 #pragma unroll
         for (int r = 0; r < L; ++r) {
           T v[L];
@@ -379,10 +455,6 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
   }
   __syncwarp();
 
-  }
-
-  cp_async_wait_group<0>();        // (copy-only path) everything staged
-  __syncwarp();
   // ---------------- stage out (what has not left yet) ----------------
   out_Sd();
   if (!early || !do_sigma) {

@@ -177,6 +177,40 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
   }
 }
 
+// One unit per record -> every GS-th global unit (record kstart + j -> global unit j * GS): the mirror of
+// rec_g2s_strided, used to write only the odd rows of an interleaved output.
+template <typename T, int UE, int GS>
+__device__ __forceinline__ void rec_s2g_strided(T* __restrict__ g, unsigned srec0, unsigned nsb, int kstart, int nunits, bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if (nunits <= 0) return;
+  const int lane = threadIdx.x & 31;
+  if constexpr ((UE % VE) == 0) {
+    if (vec_ok) {
+      constexpr int CPU = UE / VE;
+      const int total = nunits * CPU;
+      if constexpr ((32 % CPU) == 0) {
+        const unsigned j0 = (unsigned)lane / CPU, c = (unsigned)lane - j0 * CPU;
+        unsigned saddr = srec0 + (kstart + j0) * nsb + c * 16;
+        char* gp = reinterpret_cast<char*>(g) + ((size_t)j0 * GS * CPU + c) * 16;
+        const unsigned sstep = (32 / CPU) * nsb;
+        constexpr size_t gstep = (size_t)(32 / CPU) * GS * CPU * 16;
+        for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) *reinterpret_cast<int4*>(gp) = lds128_u32(saddr);
+        return;
+      }
+      for (int i = lane; i < total; i += 32) {
+        const unsigned j = (unsigned)i / CPU, c = (unsigned)i - j * CPU;
+        *reinterpret_cast<int4*>(reinterpret_cast<char*>(g) + ((size_t)j * GS * CPU + c) * 16) = lds128_u32(srec0 + (kstart + j) * nsb + c * 16);
+      }
+      return;
+    }
+  }
+  const int total = nunits * UE;
+  for (int i = lane; i < total; i += 32) {
+    const unsigned j = (unsigned)i / UE, c = (unsigned)i - j * UE;
+    g[(size_t)j * GS * UE + c] = reinterpret_cast<const T*>(__cvta_shared_to_generic(srec0 + (kstart + j) * nsb))[c];
+  }
+}
+
 // Boundary lanes (no node, no odd neighbour, no left link) get neutral operands written into their own
 // shared-memory record once, so that the dense algebra needs no per-element selects.
 template <typename T, int N>
