@@ -67,11 +67,12 @@ class FactorPack:
     def nlevels(self):
         return len(self.D)
 
-    def check(self):
-        """One device->host read: raise if any diagonal block was not positive definite."""
+    def check(self, info_host: Optional[torch.Tensor] = None):
+        """One device->host read: raise if any diagonal block was not positive definite.
+        `info_host`: this pack's info already on the host (see `DeferredCheck`)."""
         if self.info is None:
             return
-        info = self.info.cpu()
+        info = self.info.cpu() if info_host is None else info_host
         bad = torch.nonzero(info)
         if bad.numel():
             k = int(bad[0])
@@ -80,6 +81,34 @@ class FactorPack:
             raise NotPositiveDefiniteError(
                 f"cyclic reduction: diagonal block not positive definite at level {k} "
                 f"(series {flat // E}, even node {flat % E}, i.e. reduced row {2 * (flat % E)})")
+
+
+class DeferredCheck:
+    """Positive-definiteness reports of several sweeps, fetched with ONE asynchronous device->host copy
+    into pinned memory.  `wait()` blocks only until that copy is done (not until the stream is idle), so a
+    caller can queue further work behind the sweeps and look at the reports later without draining the GPU."""
+
+    def __init__(self, packs: Sequence["FactorPack"]):
+        self.packs = [p for p in packs if p is not None and p.info is not None]
+        self.host = self.event = None
+        if self.packs:
+            flat = torch.cat([p.info for p in self.packs])
+            self.host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+            self.host.copy_(flat, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+            self._keep = flat                     # the source must outlive the copy
+
+    def wait(self):
+        if self.event is None:
+            return
+        self.event.synchronize()
+        self.event = self._keep = None
+        pos = 0
+        for p in self.packs:
+            k = p.info.numel()
+            p.check(self.host[pos:pos + k])
+            pos += k
 
 
 def _alloc_levels(total_rows: Sequence[int], trailing, batch, dtype, device):

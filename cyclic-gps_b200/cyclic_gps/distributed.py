@@ -99,6 +99,23 @@ class _Ctx:
     pass
 
 
+def _finish_check(ctx, keep):
+    """Non-positive-definite reports of the (up to three) sweeps of a forward pass.  Forward-only calls look at
+    them at once (one device->host read).  When a backward pass follows (`keep`), the read is queued
+    asynchronously and looked at by `chunked_backward` after it has queued its own work: a blocking read here
+    would drain the GPU and leave it idle while the host prepares the backward pass (~0.3 ms per step)."""
+    packs = (ctx.pack, ctx.pack_tail, getattr(ctx, "bpack", None))
+    engine = ctx.engine
+    Deferred = getattr(engine, "DeferredCheck", None)
+    if keep and Deferred is not None and ctx.shape[2].type == "cuda":
+        ctx.deferred = Deferred(packs)
+    else:
+        ctx.deferred = None
+        for p in packs:
+            if p is not None:
+                p.check()
+
+
 def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, group=None, keep=False, engine=_engine):
     """Returns (mahal, logdet) as 0-dim float64 tensors (identical on every rank) and a context
     for `chunked_backward` when keep=True."""
@@ -116,7 +133,6 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
 
     width = 3 * bs + 2 * ell + 2
     S_max = max(plan.full_subchunks(r) for r in range(plan.world))
-    send = torch.zeros((S_max + 1, width), dtype=torch.float64, device=dev)
 
     def halo_blocks(first_row, count, stride):
         h = Oprev_loc[first_row:first_row + count * stride:stride].clone() if count > 0 else Oprev_loc[:0].clone()
@@ -124,7 +140,15 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
             h[0].zero_()                     # global row 0 has no predecessor
         return h
 
+    # what a rank contributes to the boundary system, one row per full sub-chunk (+ one for the ragged tail):
+    # [ R_last | y_last | halo dR | halo dy | coupling O | logdet | mahal ] in float64; built with three kernels
+    # per sweep (cat, cast, cat) -- this runs between the latency-bound ends of two sweeps
+    def boundary_rows(count, parts, pack):
+        lead = torch.cat([p.reshape(count, -1) for p in parts], dim=1).double()
+        return torch.cat([lead, pack.logdet.view(count, 1), pack.mahal.view(count, 1)], dim=1)
+
     ctx.pack = ctx.pack_tail = None
+    pieces = []
     if S > 0:
         Rb = R_loc[:S * sub].view(S, sub, ell, ell)
         xb = x_loc[:S * sub].view(S, sub, ell)
@@ -132,14 +156,10 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
         pack = engine.forward_sweep(Rb, Ob, xb, keep_factors=keep, nlevels=K, halo_O=halo_blocks(0, S, sub))
         Rl, _, yl = pack.rest
         h = pack.halo_out
-        send[:S, 0:bs] = Rl.reshape(S, bs).double()
-        send[:S, bs:bs + ell] = yl.reshape(S, ell).double()
-        send[:S, bs + ell:2 * bs + ell] = h["Rh"].reshape(S, bs).double()
-        send[:S, 2 * bs + ell:2 * bs + 2 * ell] = h["yh"].reshape(S, ell).double()
-        send[:S, 2 * bs + 2 * ell:3 * bs + 2 * ell] = h["O"].reshape(S, bs).double()
-        send[:S, -2] = pack.logdet
-        send[:S, -1] = pack.mahal
+        pieces.append(boundary_rows(S, (Rl, yl, h["Rh"], h["yh"], h["O"]), pack))
         ctx.pack = pack
+    if S < S_max:
+        pieces.append(torch.zeros((S_max - S, width), dtype=torch.float64, device=dev))
     if tail > 0:
         t0 = S * sub
         Rt = R_loc[t0:].unsqueeze(0)
@@ -147,11 +167,12 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
         Ot = Oprev_loc[t0 + 1:].unsqueeze(0)
         pack_t = engine.forward_sweep(Rt, Ot, xt, keep_factors=keep, halo_O=halo_blocks(t0, 1, 1))
         h = pack_t.halo_out
-        send[S_max, bs + ell:2 * bs + ell] = h["Rh"].reshape(bs).double()
-        send[S_max, 2 * bs + ell:2 * bs + 2 * ell] = h["yh"].reshape(ell).double()
-        send[S_max, -2] = pack_t.logdet[0]
-        send[S_max, -1] = pack_t.mahal[0]
+        zb, zv = h["Rh"].new_zeros((1, bs)), h["Rh"].new_zeros((1, ell))
+        pieces.append(boundary_rows(1, (zb, zv, h["Rh"], h["yh"], zb), pack_t))
         ctx.pack_tail = pack_t
+    else:
+        pieces.append(torch.zeros((1, width), dtype=torch.float64, device=dev))
+    send = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)       # (S_max + 1, width)
 
     allv = _gather(send, group, plan.world)                       # (world, S_max+1, width)
     # boundary system in global sub-chunk order
@@ -168,6 +189,7 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
     ctx.Sg = Sg
     if Sg == 0:
         ctx.bpack = None
+        _finish_check(ctx, keep)
         return part_mh, part_ld, ctx
     Rbnd = full[:, 0:bs].clone()
     ybnd = full[:, bs:bs + ell].clone()
@@ -183,14 +205,13 @@ def chunked_forward(R_loc, Oprev_loc, x_loc, plan: ChunkPlan, rank: int, *, grou
     Obnd = Obnd.to(dtype).contiguous().view(1, Sg - 1, ell, ell)    # (a column slice of `full` is NOT row-contiguous)
     bpack = engine.forward_sweep(Rbnd, Obnd, ybnd, keep_factors=keep)
     ctx.bpack = bpack
-    for p in (ctx.pack, ctx.pack_tail, bpack):
-        if p is not None:
-            p.check()
+    _finish_check(ctx, keep)
     return part_mh + bpack.mahal[0], part_ld + bpack.logdet[0], ctx
 
 
-def chunked_backward(ctx, g_mahal: float, g_logdet: float):
-    """Gradient of g_mahal*mahal + g_logdet*logdet wrt (R_loc, Oprev_loc, x_loc) of this rank."""
+def chunked_backward(ctx, g_mahal, g_logdet):
+    """Gradient of g_mahal*mahal + g_logdet*logdet wrt (R_loc, Oprev_loc, x_loc) of this rank.
+    The cotangents may be Python floats or 0-dim tensors (kept on the device: no host read)."""
     plan, rank, engine, S, tail = ctx.plan, ctx.rank, ctx.engine, ctx.S, ctx.tail
     (rshape, dtype, dev) = ctx.shape
     ell = rshape[-1]
@@ -218,8 +239,9 @@ def chunked_backward(ctx, g_mahal: float, g_logdet: float):
         return Sd.contiguous(), w.contiguous(), idc, ok
 
     def cot(B):
-        return (torch.full((B,), float(g_mahal), dtype=torch.float64, device=dev),
-                torch.full((B,), float(g_logdet), dtype=torch.float64, device=dev))
+        vec = lambda g: (g.detach().to(dev, torch.float64).reshape(1).expand(B).contiguous() if torch.is_tensor(g)
+                         else torch.full((B,), float(g), dtype=torch.float64, device=dev))
+        return vec(g_mahal), vec(g_logdet)
 
     if S > 0:
         Sd_h, w_h, idc, ok = halo_for(g0, S)
@@ -244,6 +266,9 @@ def chunked_backward(ctx, g_mahal: float, g_logdet: float):
         gO[t0] = So_left[0]
     if plan.rows(rank)[0] == 0 and n_loc > 0:
         gO[0].zero_()                                               # row 0 has no predecessor
+    if getattr(ctx, "deferred", None) is not None:
+        ctx.deferred.wait()                                         # raises NotPositiveDefiniteError of the forward pass
+        ctx.deferred = None
     return gR, gO, gx
 
 
@@ -263,7 +288,7 @@ class ChunkedMahalAndDet(torch.autograd.Function):
     def backward(ctx, g_mahal, g_det):
         if ctx.c is None:
             raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
-        gR, gO, gx = chunked_backward(ctx.c, float(g_mahal), float(g_det))
+        gR, gO, gx = chunked_backward(ctx.c, g_mahal, g_det)
         ctx.c = None                                   # release ~3 n l^2 elements of factors now, not at graph teardown
         return gR, gO, gx, None, None, None, None
 
