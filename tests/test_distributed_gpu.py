@@ -108,3 +108,20 @@ def test_long_series_full_size_properties():
     Jw[:-1] += torch.einsum("nji,nj->ni", O.double(), w[1:].double())
     assert float((Jw - x.double()).abs().max() / x.abs().max()) < 1e-4
     assert relerr(mm, (x.double() * w.double()).sum()) < 1e-5
+
+
+def test_chunked_not_positive_definite_is_reported():
+    """Forward-only calls raise at once; under autograd the report of the forward sweeps is read
+    asynchronously and raised by the backward pass (distributed._finish_check)."""
+    from cyclic_gps import distributed as D
+    from cyclic_gps._engine import NotPositiveDefiniteError
+    n, l = 3000, 4
+    R, O, Oprev, x = _series(n, l, torch.float32, seed=3)
+    R[1234] = -R[1234]
+    plan = D.make_plan(n, 1, sub=256)
+    with pytest.raises(NotPositiveDefiniteError):
+        D.chunked_mahal_and_det(R.cuda(), Oprev.cuda(), x.cuda(), plan, 0)
+    Rl = R.cuda().requires_grad_(True)
+    mh, ld = D.chunked_mahal_and_det(Rl, Oprev.cuda(), x.cuda(), plan, 0)
+    with pytest.raises(NotPositiveDefiniteError):
+        (mh + ld).backward()
