@@ -111,6 +111,43 @@ class DeferredCheck:
             pos += k
 
 
+class SideStream:
+    """A second CUDA stream for work that is independent of what the current stream is doing (the other half
+    of a batch of series, the ragged tail of a chunked series).  The latency-bound deep levels of one sweep
+    then run under the bandwidth-bound levels of the other.  Tensors that cross streams are registered with
+    the caching allocator (`record_stream`).  Inactive (everything stays on the current stream) on CPU tensors."""
+    _streams = {}
+
+    def __init__(self, dev: torch.device, active: bool = True):
+        self.on = bool(active) and dev.type == "cuda"
+        if self.on:
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            if key not in SideStream._streams:
+                SideStream._streams[key] = torch.cuda.Stream(device=dev)
+            self.side = SideStream._streams[key]
+            self.main = torch.cuda.current_stream(dev)
+
+    def fork(self, *inputs):
+        """The side stream may start: everything queued on the main stream so far is a dependency."""
+        if self.on:
+            self.side.wait_stream(self.main)
+            for t in inputs:
+                if t is not None:
+                    t.record_stream(self.side)
+
+    def stream(self):
+        import contextlib
+        return torch.cuda.stream(self.side) if self.on else contextlib.nullcontext()
+
+    def join(self, *outputs):
+        """The main stream waits for the side stream; `outputs` were allocated there and are used here next."""
+        if self.on:
+            self.main.wait_stream(self.side)
+            for t in outputs:
+                if t is not None:
+                    t.record_stream(self.main)
+
+
 def _alloc_levels(total_rows: Sequence[int], trailing, batch, dtype, device):
     """One flat buffer, carved into per-level (batch, rows_k, *trailing) views."""
     per = 1

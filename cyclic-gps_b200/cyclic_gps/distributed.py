@@ -99,43 +99,12 @@ class _Ctx:
     pass
 
 
-_SIDE = {}
-
-
-class _Side:
+def _Side(dev, active):
     """The ragged tail of a rank is a sweep of its own (a batch of one, ~log2(rows) latency-bound levels deep).
     It is independent of the sweep over the full sub-chunks, so on a CUDA device it runs on a second stream
     and its latency chain hides behind the bandwidth-bound levels of the main sweep (0.37 ms per step on the
-    rank that owns the tail).  Tensors crossing streams are registered with the caching allocator."""
-
-    def __init__(self, dev, active):
-        self.on = bool(active) and dev.type == "cuda"
-        if self.on:
-            key = (dev.type, dev.index)
-            if key not in _SIDE:
-                _SIDE[key] = torch.cuda.Stream(device=dev)
-            self.side = _SIDE[key]
-            self.main = torch.cuda.current_stream(dev)
-
-    def fork(self, *inputs):
-        """Side stream may start: everything queued on the main stream so far is a dependency."""
-        if self.on:
-            self.side.wait_stream(self.main)
-            for t in inputs:
-                if t is not None:
-                    t.record_stream(self.side)
-
-    def stream(self):
-        import contextlib
-        return torch.cuda.stream(self.side) if self.on else contextlib.nullcontext()
-
-    def join(self, *outputs):
-        """Main stream waits for the side stream; `outputs` were allocated there and are used here next."""
-        if self.on:
-            self.main.wait_stream(self.side)
-            for t in outputs:
-                if t is not None:
-                    t.record_stream(self.main)
+    rank that owns the tail)."""
+    return _engine.SideStream(dev, active)
 
 
 def _finish_check(ctx, keep):
