@@ -51,10 +51,10 @@ class FactorPack:
 
     def __init__(self, dtype, ell, batch, n, ms):
         self.dtype, self.ell, self.batch, self.n, self.ms = dtype, ell, batch, n, list(ms)
-        self.D: List[torch.Tensor] = []
-        self.F: List[torch.Tensor] = []
-        self.G: List[torch.Tensor] = []
-        self.X: List[Optional[torch.Tensor]] = []
+        # per-level lists D, F, G, X: (B, rows_k, ...) views of the packed buffers, built on first use (a sweep
+        # itself only needs the packed buffers; creating ~4 L views costs more host time than a small sweep)
+        self._levels = {}
+        self._specs = {}
         self.G_halo: List[torch.Tensor] = []
         self.D_flat = self.F_flat = self.G_flat = self.X_flat = self.G_halo_flat = None   # packed storage behind the lists
         self.logdet: Optional[torch.Tensor] = None     # (B,) float64: 2 * sum log diag
@@ -65,7 +65,26 @@ class FactorPack:
 
     @property
     def nlevels(self):
-        return len(self.D)
+        return len(self.ms)
+
+    @property
+    def device(self):
+        return self.D_flat.device if self.D_flat is not None else self.D[0].device
+
+    def _get(self, name):
+        if name not in self._levels:
+            spec = self._specs.get(name)
+            if spec is None:
+                self._levels[name] = []
+            else:
+                flat, rows, trailing = spec
+                self._levels[name] = [None] * len(rows) if flat is None else _carve(flat, rows, trailing, self.batch)
+        return self._levels[name]
+
+    D = property(lambda self: self._get("D"), lambda self, v: self._levels.__setitem__("D", v))
+    F = property(lambda self: self._get("F"), lambda self, v: self._levels.__setitem__("F", v))
+    G = property(lambda self: self._get("G"), lambda self, v: self._levels.__setitem__("G", v))
+    X = property(lambda self: self._get("X"), lambda self, v: self._levels.__setitem__("X", v))
 
     def check(self, info_host: Optional[torch.Tensor] = None):
         """One device->host read: raise if any diagonal block was not positive definite.
@@ -148,18 +167,53 @@ class SideStream:
                     t.record_stream(self.main)
 
 
+def _carve(flat, total_rows: Sequence[int], trailing, batch):
+    """Per-level (batch, rows_k, *trailing) views of a packed buffer."""
+    per = 1
+    for t in trailing:
+        per *= t
+    views, pos = [], 0
+    for r in total_rows:
+        size = batch * r * per
+        views.append(flat[pos:pos + size].view(batch, r, *trailing))
+        pos += size
+    return views
+
+
 def _alloc_levels(total_rows: Sequence[int], trailing, batch, dtype, device):
     """One flat buffer, carved into per-level (batch, rows_k, *trailing) views."""
     per = 1
     for t in trailing:
         per *= t
-    sizes = [batch * r * per for r in total_rows]
-    flat = torch.empty(sum(sizes), dtype=dtype, device=device)
-    views, pos = [], 0
-    for r, s in zip(total_rows, sizes):
-        views.append(flat[pos:pos + s].view(batch, r, *trailing))
-        pos += s
-    return flat, views
+    flat = torch.empty(batch * sum(total_rows) * per, dtype=dtype, device=device)
+    return flat, _carve(flat, total_rows, trailing, batch)
+
+
+def _flat_only(total_rows: Sequence[int], trailing, batch, dtype, device):
+    per = 1
+    for t in trailing:
+        per *= t
+    return torch.empty(batch * sum(total_rows) * per, dtype=dtype, device=device)
+
+
+class _Workspace:
+    """Scratch buffers of one sweep carved out of ONE allocation and handed to the library as raw addresses
+    (no per-buffer tensor objects: on small problems the host, not the GPU, is the bottleneck)."""
+
+    def __init__(self, sizes_bytes: Sequence[int], device, zero: bool = False):
+        offs, pos = [], 0
+        for sz in sizes_bytes:
+            offs.append(pos)
+            pos += (sz + 255) & ~255
+        self.buf = (torch.zeros if zero else torch.empty)(max(pos, 1), dtype=torch.uint8, device=device)
+        base = self.buf.data_ptr()
+        self.sizes = list(sizes_bytes)
+        self.offs = offs
+        self.ptrs = [base + o if sz > 0 else None for o, sz in zip(offs, sizes_bytes)]
+
+    def view(self, i, dtype, shape):
+        sz = self.sizes[i]
+        return self.buf[self.offs[i]:self.offs[i] + sz].view(dtype).view(shape)
 
 
 def _rows_contiguous(t):
@@ -190,25 +244,25 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
     Es = [counts(m)[0] for m in ms]
     os_ = [counts(m)[1] for m in ms]
     gs = [counts(m)[2] for m in ms]
+    es = torch.empty((), dtype=dtype).element_size()
     if keep_factors:
-        pack.D_flat, pack.D = _alloc_levels(Es, (ell, ell), B, dtype, dev)
-        pack.F_flat, pack.F = _alloc_levels(os_, (ell, ell), B, dtype, dev)
-        pack.G_flat, pack.G = _alloc_levels(gs, (ell, ell), B, dtype, dev)
+        pack.D_flat = _flat_only(Es, (ell, ell), B, dtype, dev)
+        pack.F_flat = _flat_only(os_, (ell, ell), B, dtype, dev)
+        pack.G_flat = _flat_only(gs, (ell, ell), B, dtype, dev)
     else:
         pack.D_flat = pack.F_flat = pack.G_flat = None
-        pack.D = [None] * L
-        pack.F = [None] * L
-        pack.G = [None] * L
-    if y is not None and keep_factors:
-        pack.X_flat, pack.X = _alloc_levels(Es, (ell,), B, dtype, dev)
-    else:
-        pack.X_flat = None
-        pack.X = [None] * L
-    # scalar accumulators: (B, ACC_SLOTS) so that the per-CTA atomics of a long series do not all hit one address
+    pack._specs["D"] = (pack.D_flat, Es, (ell, ell))
+    pack._specs["F"] = (pack.F_flat, os_, (ell, ell))
+    pack._specs["G"] = (pack.G_flat, gs, (ell, ell))
+    pack.X_flat = _flat_only(Es, (ell,), B, dtype, dev) if (y is not None and keep_factors) else None
+    pack._specs["X"] = (pack.X_flat, Es, (ell,))
+    # scalar accumulators: (B, ACC_SLOTS) so that the per-CTA atomics of a long series do not all hit one address;
+    # they and the per-level failure words share one zero-filled allocation
     slots = ACC_SLOTS if n >= 4096 else 1
-    acc_ld = torch.zeros((B, slots), dtype=torch.float64, device=dev) if want_logdet else None
-    acc_mh = torch.zeros((B, slots), dtype=torch.float64, device=dev) if y is not None else None
-    pack.info = torch.zeros(L, dtype=torch.int32, device=dev)
+    zws = _Workspace([B * slots * 8 if want_logdet else 0, B * slots * 8 if y is not None else 0, L * 4], dev, zero=True)
+    acc_ld = zws.view(0, torch.float64, (B, slots)) if want_logdet else None
+    acc_mh = zws.view(1, torch.float64, (B, slots)) if y is not None else None
+    pack.info = zws.view(2, torch.int32, (L,))
     halo = halo_O is not None
     Rh = yh = None
     pack.G_halo_flat = None
@@ -221,13 +275,13 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
         halo_O = halo_O.contiguous()
     # ping-pong scratch for the reduced systems: slot 0 <- levels 0,2,.. ; slot 1 <- levels 1,3,..
     r0, r1 = n // 2, n // 4
-    scrR = (torch.empty((B * r0, ell, ell), dtype=dtype, device=dev) if r0 else None,
-            torch.empty((B * r1, ell, ell), dtype=dtype, device=dev) if r1 else None)
-    scrO = (torch.empty((B * r0, ell, ell), dtype=dtype, device=dev) if r0 > 1 else None,
-            torch.empty((B * r1, ell, ell), dtype=dtype, device=dev) if r1 > 1 else None)
-    scry = (torch.empty((B * r0, ell), dtype=dtype, device=dev) if (r0 and y is not None) else None,
-            torch.empty((B * r1, ell), dtype=dtype, device=dev) if (r1 and y is not None) else None)
-    On_h = (torch.empty((B, ell, ell), dtype=dtype, device=dev), torch.empty((B, ell, ell), dtype=dtype, device=dev)) if halo else (None, None)
+    has_y = y is not None
+    ws = _Workspace([B * r0 * bs * es, B * r1 * bs * es,                                   # scrR
+                     B * r0 * bs * es if r0 > 1 else 0, B * r1 * bs * es if r1 > 1 else 0,  # scrO
+                     B * r0 * ell * es if has_y else 0, B * r1 * ell * es if has_y else 0,  # scry
+                     B * bs * es if halo else 0, B * bs * es if halo else 0], dev)          # On_halo
+    pack._ws = ws                                       # keeps `rest` / `halo_out` views alive
+    scrR, scrO, scry, On_h = ws.ptrs[0:2], ws.ptrs[2:4], ws.ptrs[4:6], ws.ptrs[6:8]
     sR, sO = R.stride(0), (O.stride(0) if O.shape[1] > 0 else 0)
     sy = y.stride(0) if y is not None else 0
 
@@ -239,6 +293,11 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
                           scrR=scrR, scrO=scrO, scry=scry, logdet=acc_ld, mahal=acc_mh, acc_slots=slots, info=pack.info,
                           O_halo=halo_O, G_halo=pack.G_halo_flat, On_halo=On_h, Rh_acc=Rh, yh_acc=yh)
     else:
+        shp = lambda i, rows, *tr: ws.view(i, dtype, (B * rows,) + tr) if ws.sizes[i] else None
+        scrR = (shp(0, r0, ell, ell), shp(1, r1, ell, ell))
+        scrO = (shp(2, r0, ell, ell), shp(3, r1, ell, ell))
+        scry = (shp(4, r0, ell), shp(5, r1, ell))
+        On_h = (shp(6, 1, ell, ell), shp(7, 1, ell, ell))
         cur_R, cur_O, cur_y, cur_halo = R, O, y, halo_O
         for k, m in enumerate(ms):
             E, o, g = counts(m)
@@ -255,16 +314,20 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
             _native.level_fwd(dtype, ell, **fields)
             cur_R, cur_O, cur_y = fields["Rn"], fields["On"], fields["yn"]
             sR, sO, sy = o * bs, max(o - 1, 0) * bs, o * ell
-    pack.mahal = acc_mh.sum(dim=1) if acc_mh is not None else None
-    pack.logdet = acc_ld.sum(dim=1).mul_(2.0) if acc_ld is not None else None   # log|J| = 2 sum log diag(K)  (reference :458, :438)
+    if slots == 1:
+        pack.mahal = acc_mh.view(B) if acc_mh is not None else None
+        pack.logdet = acc_ld.view(B).mul_(2.0) if acc_ld is not None else None
+    else:
+        pack.mahal = acc_mh.sum(dim=1) if acc_mh is not None else None
+        pack.logdet = acc_ld.sum(dim=1).mul_(2.0) if acc_ld is not None else None   # log|J| = 2 sum log diag(K)  (reference :458, :438)
     last = (L - 1) & 1
     if L < len(ms_all):
         o = ms[-1] // 2
-        pack.rest = (scrR[last][:B * o].view(B, o, ell, ell),
-                     scrO[last][:B * (o - 1)].view(B, o - 1, ell, ell) if o > 1 else None,
-                     scry[last][:B * o].view(B, o, ell) if y is not None else None)
+        pack.rest = (ws.view(last, dtype, (B * (r1 if last else r0), ell, ell))[:B * o].view(B, o, ell, ell),
+                     ws.view(2 + last, dtype, (B * (r1 if last else r0), ell, ell))[:B * (o - 1)].view(B, o - 1, ell, ell) if o > 1 else None,
+                     ws.view(4 + last, dtype, (B * (r1 if last else r0), ell))[:B * o].view(B, o, ell) if y is not None else None)
     if halo:
-        pack.halo_out = dict(Rh=Rh, yh=yh, O=On_h[last])
+        pack.halo_out = dict(Rh=Rh, yh=yh, O=ws.view(6 + last, dtype, (B, ell, ell)))
     return pack
 
 
@@ -284,7 +347,7 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
     out   optional (Sd, So, w) tensors to write level 0 into: (B,m,l,l), (B,m-1,l,l), (B,m,l), any batch
           stride, rows contiguous"""
     B, ell, dtype = pack.batch, pack.ell, pack.dtype
-    dev = pack.D[0].device
+    dev = pack.device
     bs = ell * ell
     L = pack.nlevels
     n = pack.ms[0]
@@ -312,12 +375,14 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
         wv = torch.empty((B, n, ell), dtype=dtype, device=dev) if w else None
     m1 = pack.ms[1] if L > 1 else 0
     m2 = pack.ms[2] if L > 2 else 0
-    mk = lambda rows, *tr: torch.empty((B * rows,) + tr, dtype=dtype, device=dev) if rows else None
-    scrSd = (mk(m2, ell, ell) if sigma else None, mk(m1, ell, ell) if sigma else None)
-    scrSo = (mk(m2, ell, ell) if sigma else None, mk(m1, ell, ell) if sigma else None)
-    scrw = (mk(m2, ell) if w else None, mk(m1, ell) if w else None)
+    es = torch.empty((), dtype=dtype).element_size()
     use_halo = halo is not None
-    So_h = (torch.empty((B, ell, ell), dtype=dtype, device=dev), torch.empty((B, ell, ell), dtype=dtype, device=dev)) if (use_halo and sigma) else (None, None)
+    hs = B * bs * es if (use_halo and sigma) else 0
+    # ping-pong scratch of the descending (Sigma_d, Sigma_o, w), slot [1] <- odd levels, slot [0] <- even levels >= 2
+    ws = _Workspace([B * m2 * bs * es if sigma else 0, B * m1 * bs * es if sigma else 0,
+                     B * m2 * bs * es if sigma else 0, B * m1 * bs * es if sigma else 0,
+                     B * m2 * ell * es if w else 0, B * m1 * ell * es if w else 0, hs, hs], dev)
+    scrSd, scrSo, scrw, So_h = ws.ptrs[0:2], ws.ptrs[2:4], ws.ptrs[4:6], ws.ptrs[6:8]
     So_h_out = torch.empty((B, ell, ell), dtype=dtype, device=dev) if (use_halo and sigma) else None
     gm, gd = (grad if grad is not None else (None, None))
     stride0 = lambda t, default: (t.stride(0) if (t is not None and t.dim() > 1 and t.shape[0] > 1) else default)
@@ -334,6 +399,11 @@ def backward_sweep(pack: FactorPack, *, sigma: bool, w: bool, xs: Optional[Seque
                           w_halo=halo["w"].contiguous() if (use_halo and w) else None,
                           So_halo_in=halo["So"].contiguous() if (use_halo and sigma) else None, So_halo=So_h, So_halo_out=So_h_out)
     else:
+        shp = lambda i, rows, *tr: ws.view(i, dtype, (B * rows,) + tr) if ws.sizes[i] else None
+        scrSd = (shp(0, m2, ell, ell), shp(1, m1, ell, ell))
+        scrSo = (shp(2, m2, ell, ell), shp(3, m1, ell, ell))
+        scrw = (shp(4, m2, ell), shp(5, m1, ell))
+        So_h = (shp(6, 1, ell, ell), shp(7, 1, ell, ell))
         Sd_in, So_in, w_in = top_Sd, top_So, top_w
         so_h = halo["So"].contiguous() if (use_halo and sigma) else None
         for k in range(L - 1, -1, -1):

@@ -135,8 +135,8 @@ def dtype_code(dtype: torch.dtype) -> int:
 
 
 def _ptr(t):
-    if t is None:
-        return None
+    if t is None or isinstance(t, int):      # raw device address (engine workspaces)
+        return t
     if not t.is_cuda:
         raise RuntimeError("internal error: CPU tensor handed to the native CR library")
     return t.data_ptr()

@@ -306,7 +306,7 @@ class _LogDetFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         pack = ctx.pack
-        dev = pack.D[0].device
+        dev = pack.device
         gd = g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
         gm = torch.zeros_like(gd)
         gR, gO, _ = _engine.backward_sweep(pack, sigma=True, w=False, grad=(gm, gd))
@@ -349,7 +349,7 @@ class _MahalAndDetFn(torch.autograd.Function):
         pack = ctx.pack
         if pack is None:
             raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
-        dev = pack.D[0].device
+        dev = pack.device
         as_vec = lambda g: g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
         gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(as_vec(g_mahal), as_vec(g_det)))
         ctx.pack = None                                # free the packed factors (~3 n l^2 elements) right away
