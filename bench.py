@@ -200,7 +200,7 @@ def run_reference(args):
                                            "one series at a time"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_long(args):
@@ -303,9 +303,32 @@ def run_long(args):
                        "l2": "inputs per step exceed L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "gpu_launches": len(trace.records) // max(min(args.steps, 2), 1) * args.steps,
             "clocks": clk, "loglik": float(ll)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun children) write to fd 1; the driver wants ONE JSON line there.
+    From here on fd 1 points at stderr and `emit` writes the line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -326,6 +349,7 @@ def main():
     ap.add_argument("--sub", type=int, default=None, help="long workload: rows per sub-chunk (power of two)")
     ap.add_argument("--variant", type=int, default=0, help="force a kernel family (0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "long":
@@ -530,7 +554,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step, "clocks": clk,
             "loglik_checksum": float(total) / max(args.steps, 1)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
