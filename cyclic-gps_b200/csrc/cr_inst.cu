@@ -12,6 +12,9 @@
 #define CRB_HAVE_TPN 0
 #endif
 #include "cr_halfsolve.cuh"
+#if !CRB_HAVE_TPN
+#include "cr_tpn_common.cuh"   // MultiArgs
+#endif
 
 #define CRB_CAT_(a, b, c, d) a##_##b##_##c##_##d
 #define CRB_CAT(a, b, c, d) CRB_CAT_(a, b, c, d)
@@ -25,6 +28,8 @@ cudaError_t CRB_CAT(inst_bwd, CRB_TN, CRB_LO, CRB_HI)(int, const LevelBwdArgs&, 
 cudaError_t CRB_CAT(inst_hs, CRB_TN, CRB_LO, CRB_HI)(int, const HalfSolveArgs&, cudaStream_t) { return cudaErrorNotSupported; }
 int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
 int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int) { return 0; }
+cudaError_t CRB_CAT(inst_fwd_multi, CRB_TN, CRB_LO, CRB_HI)(int, const MultiArgs<LevelFwdArgs>*, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t CRB_CAT(inst_bwd_multi, CRB_TN, CRB_LO, CRB_HI)(int, const MultiArgs<LevelBwdArgs>*, cudaStream_t) { return cudaErrorNotSupported; }
 #else
 
 #if CRB_HAVE_TPN
@@ -85,6 +90,21 @@ struct Dispatch {
     if (ell == L) return launch_level_halfsolve<CRB_T, L>(a, s);
     return Dispatch<L + 1>::hs(ell, a, s);
   }
+  // fused deep levels (thread-per-node family only); a == nullptr asks whether the kernel exists
+  static cudaError_t fwd_multi(int ell, const MultiArgs<LevelFwdArgs>* a, cudaStream_t s) {
+    if (ell != L) return Dispatch<L + 1>::fwd_multi(ell, a, s);
+#if CRB_HAVE_TPN
+    if constexpr (TpnFwdCfg<CRB_T, L>::ELIGIBLE) return a == nullptr ? cudaSuccess : launch_tpn_fwd_multi<CRB_T, L>(*a, s);
+#endif
+    return cudaErrorNotSupported;
+  }
+  static cudaError_t bwd_multi(int ell, const MultiArgs<LevelBwdArgs>* a, cudaStream_t s) {
+    if (ell != L) return Dispatch<L + 1>::bwd_multi(ell, a, s);
+#if CRB_HAVE_TPN
+    if constexpr (TpnBwdCfg<CRB_T, L>::ELIGIBLE) return a == nullptr ? cudaSuccess : launch_tpn_bwd_multi<CRB_T, L>(*a, s);
+#endif
+    return cudaErrorNotSupported;
+  }
   static int fwd_tile(int ell) {
     if (ell != L) return Dispatch<L + 1>::fwd_tile(ell);
 #if CRB_HAVE_TPN
@@ -109,6 +129,8 @@ struct Dispatch<CRB_HI + 1> {
   static cudaError_t hs(int, const HalfSolveArgs&, cudaStream_t) { return cudaErrorInvalidValue; }
   static int fwd_tile(int) { return 0; }
   static int bwd_tile(int) { return 0; }
+  static cudaError_t fwd_multi(int, const MultiArgs<LevelFwdArgs>*, cudaStream_t) { return cudaErrorNotSupported; }
+  static cudaError_t bwd_multi(int, const MultiArgs<LevelBwdArgs>*, cudaStream_t) { return cudaErrorNotSupported; }
 };
 
 cudaError_t CRB_CAT(inst_fwd, CRB_TN, CRB_LO, CRB_HI)(int ell, const LevelFwdArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::fwd(ell, a, s); }
@@ -116,6 +138,8 @@ cudaError_t CRB_CAT(inst_bwd, CRB_TN, CRB_LO, CRB_HI)(int ell, const LevelBwdArg
 cudaError_t CRB_CAT(inst_hs, CRB_TN, CRB_LO, CRB_HI)(int ell, const HalfSolveArgs& a, cudaStream_t s) { return Dispatch<CRB_LO>::hs(ell, a, s); }
 int CRB_CAT(inst_fwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::fwd_tile(ell); }
 int CRB_CAT(inst_bwd_tile, CRB_TN, CRB_LO, CRB_HI)(int ell) { return Dispatch<CRB_LO>::bwd_tile(ell); }
+cudaError_t CRB_CAT(inst_fwd_multi, CRB_TN, CRB_LO, CRB_HI)(int ell, const MultiArgs<LevelFwdArgs>* a, cudaStream_t s) { return Dispatch<CRB_LO>::fwd_multi(ell, a, s); }
+cudaError_t CRB_CAT(inst_bwd_multi, CRB_TN, CRB_LO, CRB_HI)(int ell, const MultiArgs<LevelBwdArgs>* a, cudaStream_t s) { return Dispatch<CRB_LO>::bwd_multi(ell, a, s); }
 #endif  // CRB_STUB
 
 }  // namespace crb200

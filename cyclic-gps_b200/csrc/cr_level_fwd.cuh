@@ -42,7 +42,10 @@ struct FwdCfg {
   static constexpr int BS = L * L;
   static constexpr int NODE_ELEMS = 6 * BS + 3 * L;
   static constexpr int GRAN = 32 / LG;  // groups per warp: NG must be a multiple
-  static constexpr int NG_FIT = (100 * 1024) / (NODE_ELEMS * (int)sizeof(T));
+  // shared-memory budget per CTA: 100 KB (two CTAs per SM), or 200 KB when fewer than four nodes would fit in 100 KB
+  // (fp64 ell >= 24): every CTA recomputes one halo node, so with NG = 2 half of the work would be redundant
+  static constexpr int CAP = (4 * NODE_ELEMS * (int)sizeof(T) > 100 * 1024) ? 200 * 1024 : 100 * 1024;
+  static constexpr int NG_FIT = CAP / (NODE_ELEMS * (int)sizeof(T));
   static constexpr int NG_RAW = cmin(kThreads / LG, NG_FIT);
   static constexpr int NG = cmax(cmax(2, GRAN), (NG_RAW / GRAN) * GRAN);
   static constexpr int THREADS = NG * LG;

@@ -50,26 +50,19 @@ struct TpnBwdCfg {
 };
 
 
+// One tile (NT even nodes of series b starting at node tile * NT) by one warp; see tpn_fwd_tile.
 template <typename T, int L>
-__global__ void __launch_bounds__(32 * TpnBwdCfg<T, L>::NW, TpnBwdCfg<T, L>::MIN_CTAS)
-cr_tpn_bwd_kernel(const LevelBwdArgs a) {
+__device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned char* smem_warp, const int b, const int tile) {
   using Cf = TpnBwdCfg<T, L>;
   constexpr int BS = Cf::BS, NS = Cf::NS, NT = Cf::NT;
   constexpr unsigned ES = sizeof(T);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  T* S = reinterpret_cast<T*>(smem_raw + (size_t)warp * TpnBwdCfg<T, L>::SMEM_W);
+  T* S = reinterpret_cast<T*>(smem_warp);
   const unsigned s0 = smem_u32(S);
   const unsigned nsb = NS * ES;
   const unsigned rec1 = s0 + nsb;
 
   const int m = a.m;
   const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
-  const int tiles = (E + NT - 1) / NT;
-  const long long vb = (long long)blockIdx.x * TpnBwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
-  if (vb >= (long long)tiles * a.batch) return;
-  const int b = (int)(vb / tiles);
-  const int tile = (int)(vb - (long long)b * tiles);
   const int e0 = tile * NT;
   const int nE = cmin(NT, E - e0);
   const bool do_sigma = a.Sd_out != nullptr;
@@ -464,6 +457,38 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 }
 
 template <typename T, int L>
+__global__ void __launch_bounds__(32 * TpnBwdCfg<T, L>::NW, TpnBwdCfg<T, L>::MIN_CTAS)
+cr_tpn_bwd_kernel(const LevelBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int E = (a.m + 1) >> 1;
+  const int tiles = (E + TpnBwdCfg<T, L>::NT - 1) / TpnBwdCfg<T, L>::NT;
+  const long long vb = (long long)blockIdx.x * TpnBwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
+  if (vb >= (long long)tiles * a.batch) return;
+  const int b = (int)(vb / tiles);
+  tpn_bwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnBwdCfg<T, L>::SMEM_W, b, (int)(vb - (long long)b * tiles));
+}
+
+// Deep levels fused (deepest first): one CTA per series, see cr_tpn_fwd_multi_kernel.
+template <typename T, int L>
+__global__ void __launch_bounds__(32 * kMultiWarps, 1)
+cr_tpn_bwd_multi_kernel(const __grid_constant__ MultiArgs<LevelBwdArgs> ma) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  for (int k = 0; k < ma.count; ++k) {
+    const LevelBwdArgs& a = ma.lv[k];
+    const int E = (a.m + 1) >> 1;
+    const int tiles = (E + TpnBwdCfg<T, L>::NT - 1) / TpnBwdCfg<T, L>::NT;
+    for (int tile = warp; tile < tiles; tile += kMultiWarps) {
+      tpn_bwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnBwdCfg<T, L>::SMEM_W, b, tile);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int L>
 cudaError_t launch_tpn_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   using C = TpnBwdCfg<T, L>;
   static bool attr_done[64] = {false};
@@ -481,6 +506,23 @@ cudaError_t launch_tpn_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   const long long grid = (total + C::NW - 1) / C::NW;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   cr_tpn_bwd_kernel<T, L><<<(unsigned)grid, 32 * C::NW, C::SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T, int L>
+cudaError_t launch_tpn_bwd_multi(const MultiArgs<LevelBwdArgs>& ma, cudaStream_t stream) {
+  using C = TpnBwdCfg<T, L>;
+  constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(cr_tpn_bwd_multi_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
+  cr_tpn_bwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 // LDS.128 + STG.128, two integer ops, loop control).
 #pragma once
 #include "cr_common.cuh"
+#include "cr_multi.h"
 
 #ifndef CRB200_SMEM_PAD
 #define CRB200_SMEM_PAD 0      // extra dynamic shared memory per CTA (lowers the CTAs/SM; profiling experiments)

@@ -40,25 +40,19 @@ struct TpnFwdCfg {
   static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((224 * 1024) / (SMEM + 1024))));
 };
 
+// One tile (OWN even nodes of series b starting at node tile * OWN) by one warp; `smem_warp` is this warp's
+// SMEM_W bytes.  Called by the level kernel (one tile per warp) and by the fused deep-level kernel.
 template <typename T, int L>
-__global__ void __launch_bounds__(32 * TpnFwdCfg<T, L>::NW, TpnFwdCfg<T, L>::MIN_CTAS)
-cr_tpn_fwd_kernel(const LevelFwdArgs a) {
+__device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned char* smem_warp, const int b, const int tile) {
   using C = TpnFwdCfg<T, L>;
   constexpr int BS = C::BS, NS = C::NS, NT = C::NT, OWN = C::OWN;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  T* S = reinterpret_cast<T*>(smem_raw + (size_t)warp * TpnFwdCfg<T, L>::SMEM_W);
+  T* S = reinterpret_cast<T*>(smem_warp);
   constexpr unsigned ES = sizeof(T);
   const unsigned s0 = smem_u32(S);
   const unsigned nsb = NS * ES;
 
   const int m = a.m;
   const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
-  const int tiles = (E + OWN - 1) / OWN;
-  const long long vb = (long long)blockIdx.x * TpnFwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
-  if (vb >= (long long)tiles * a.batch) return;
-  const int b = (int)(vb / tiles);
-  const int tile = (int)(vb - (long long)b * tiles);
   const int e0 = tile * OWN;
   const bool has_y = a.y != nullptr;
   const bool halo = a.O_halo != nullptr;
@@ -395,6 +389,40 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
 }
 
 template <typename T, int L>
+__global__ void __launch_bounds__(32 * TpnFwdCfg<T, L>::NW, TpnFwdCfg<T, L>::MIN_CTAS)
+cr_tpn_fwd_kernel(const LevelFwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int E = (a.m + 1) >> 1;
+  const int tiles = (E + TpnFwdCfg<T, L>::OWN - 1) / TpnFwdCfg<T, L>::OWN;
+  const long long vb = (long long)blockIdx.x * TpnFwdCfg<T, L>::NW + warp;   // virtual block = one warp's tile
+  if (vb >= (long long)tiles * a.batch) return;
+  const int b = (int)(vb / tiles);
+  tpn_fwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnFwdCfg<T, L>::SMEM_W, b, (int)(vb - (long long)b * tiles));
+}
+
+// Deep levels fused: ONE CTA per series runs levels lv[0..count) back to back, its warps sharing the tiles of a
+// level; levels communicate through global memory (L2) and a __syncthreads.  Used by crb200_sweep_fwd for the
+// levels with only a few tiles per series, where a launch per level costs more than its work.
+template <typename T, int L>
+__global__ void __launch_bounds__(32 * kMultiWarps, 1)
+cr_tpn_fwd_multi_kernel(const __grid_constant__ MultiArgs<LevelFwdArgs> ma) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  for (int k = 0; k < ma.count; ++k) {
+    const LevelFwdArgs& a = ma.lv[k];
+    const int E = (a.m + 1) >> 1;
+    const int tiles = (E + TpnFwdCfg<T, L>::OWN - 1) / TpnFwdCfg<T, L>::OWN;
+    for (int tile = warp; tile < tiles; tile += kMultiWarps) {
+      tpn_fwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnFwdCfg<T, L>::SMEM_W, b, tile);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int L>
 cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   using C = TpnFwdCfg<T, L>;
   static bool attr_done[64] = {false};
@@ -412,6 +440,23 @@ cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   const long long grid = (total + C::NW - 1) / C::NW;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   cr_tpn_fwd_kernel<T, L><<<(unsigned)grid, 32 * C::NW, C::SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T, int L>
+cudaError_t launch_tpn_fwd_multi(const MultiArgs<LevelFwdArgs>& ma, cudaStream_t stream) {
+  using C = TpnFwdCfg<T, L>;
+  constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(cr_tpn_fwd_multi_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
+  cr_tpn_fwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
   return cudaGetLastError();
 }
 

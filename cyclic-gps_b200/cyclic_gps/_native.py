@@ -81,7 +81,7 @@ class SweepHsArgs(C.Structure):
 
 EXPORTS = ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
            "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd", "crb200_sweep_halfsolve",
-           "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes")
+           "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_launch_count")
 
 _lib = None
 _lock = threading.Lock()
@@ -119,6 +119,8 @@ def load():
         lib.crb200_sweep_halfsolve.argtypes = [_i, _i, C.POINTER(SweepHsArgs), _vp]
         lib.crb200_sweep_bwd.restype = _i
         lib.crb200_sweep_bwd.argtypes = [_i, _i, C.POINTER(SweepBwdArgs), _vp]
+        lib.crb200_launch_count.restype = C.c_longlong
+        lib.crb200_launch_count.argtypes = []
         for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
             getattr(lib, name).restype = _i
             getattr(lib, name).argtypes = [_i, _i]
@@ -221,6 +223,11 @@ def sweep_bwd(dtype: torch.dtype, ell: int, **fields):
 def sweep_halfsolve(dtype: torch.dtype, ell: int, **fields):
     a = _fill(SweepHsArgs(), fields)
     _check(load().crb200_sweep_halfsolve(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_halfsolve")
+
+
+def launch_count() -> int:
+    """Kernels launched by libcrb200 in this process so far."""
+    return int(load().crb200_launch_count())
 
 
 def tracing() -> bool:

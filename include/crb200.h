@@ -3,7 +3,8 @@
  * Drop-in boundary for the hot path of cunningham-lab/cyclic-gps: the module-level
  * functions of cyclic_gps/cyclic_reduction.py (the reference has no FFI; its "interface" is
  * that Python module, imported at cyclic_gps/models.py:10).  Each entry below names the
- * reference code it replaces.  The library allocates nothing, keeps no global state, takes
+ * reference code it replaces.  The library allocates nothing, keeps no global state (apart from
+ * a diagnostic launch counter), takes
  * raw DEVICE pointers plus a cudaStream_t (as void*), is re-entrant and may be called from any
  * host thread (the autograd engine calls the backward entries from its own thread).
  *
@@ -92,7 +93,12 @@ typedef struct crb200_hs_args {
 } crb200_hs_args;
 
 /* Whole sweeps: the level loop runs inside the library (one host call, ~3 us per level instead of a
- * Python round trip).  Packed per-level storage: level k of a family starts at element offset
+ * Python round trip).  With variant = CRB200_AUTO the deep levels of a sweep (a series has at most 8 tiles, level >= 3)
+ * run as ONE fused launch where the thread-per-node family exists: one CTA per series walks those levels, writing
+ * every level's intermediate result at its own offset inside the scratch buffers described below (they are large
+ * enough as specified); the results the caller reads back sit where they are documented to sit.  Only batches of at
+ * most two series per SM are fused (every series keeps a CTA for the whole tail).
+ * Packed per-level storage: level k of a family starts at element offset
  * batch * unit * sum_{j<k} rows_j  with rows_j = E_j (D, X), o_j (F), g_j (G) and unit = l*l (l for X);
  * m_0 = n, m_{k+1} = floor(m_k / 2).  Ping-pong scratch: level k writes its result to slot [k & 1].
  *
@@ -146,6 +152,8 @@ int crb200_version(void);
 int crb200_max_ell(void);
 /* cudaError_t of the last failing launch on the calling thread's most recent call (0 if none). */
 int crb200_last_cuda_error(void);
+/* Diagnostic: number of kernels this library has launched in the process so far (bench.py's gpu_launches). */
+long long crb200_launch_count(void);
 
 int crb200_level_fwd(int dtype, int ell, const crb200_fwd_args* args, void* stream);
 int crb200_level_bwd(int dtype, int ell, const crb200_bwd_args* args, void* stream);
