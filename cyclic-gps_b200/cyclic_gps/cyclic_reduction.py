@@ -323,6 +323,14 @@ def det(decomp):
     return 2 * total
 
 
+# Under autograd the positive-definiteness report of the forward sweep is fetched asynchronously and raised by the
+# backward pass (after it has queued its kernels): a blocking device->host read at the end of the forward pass drains
+# the GPU and leaves it idle while the host walks from forward to backward (0.1-0.6 ms per step on configs[1],
+# depending on the host).  Forward-only calls always check at once.  Set EAGER_PD_CHECK = True to get the
+# reference's behaviour (NotPSDError raised inside mahal_and_det, cyclic_reduction.py:429) under autograd too.
+EAGER_PD_CHECK = False
+
+
 class _MahalAndDetFn(torch.autograd.Function):
     """(x^T J^{-1} x, log|J|) in one forward sweep; backward = back-solve + selected inverse
     with the gradient assembled inside the level-0 kernel."""
@@ -335,7 +343,11 @@ class _MahalAndDetFn(torch.autograd.Function):
         X = _batched(_dev(x, dev, Rs.dtype), batched)
         need = any(ctx.needs_input_grad[:3])
         pack = _engine.forward_sweep(R, O, X, keep_factors=need)
-        pack.check()
+        if need and not EAGER_PD_CHECK:
+            ctx.deferred = _engine.DeferredCheck([pack])
+        else:
+            ctx.deferred = None
+            pack.check()
         ctx.pack = pack if need else None
         ctx.batched, ctx.devs = batched, (Rs.device, Os.device, x.device)
         mh, ld = pack.mahal.to(Rs.dtype), pack.logdet.to(Rs.dtype)
@@ -353,6 +365,9 @@ class _MahalAndDetFn(torch.autograd.Function):
         as_vec = lambda g: g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
         gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(as_vec(g_mahal), as_vec(g_det)))
         ctx.pack = None                                # free the packed factors (~3 n l^2 elements) right away
+        if ctx.deferred is not None:
+            deferred, ctx.deferred = ctx.deferred, None
+            deferred.wait()                            # NotPositiveDefiniteError of the forward sweep surfaces here
         b = ctx.batched
         return (_to_caller(gR, b, ctx.devs[0]), _to_caller(gO, b, ctx.devs[1]), _to_caller(gx, b, ctx.devs[2]), None)
 

@@ -362,3 +362,23 @@ def test_config2_shape_properties():
         dec_o = orc.factor(R[b].double().cpu(), O[b].double().cpu())
         assert_close(dd[b], orc.logdet(dec_o), 1e-4)
         assert_close(w[b], orc.solve(dec_o, x[b].double().cpu()), 1e-4)
+
+
+def test_not_positive_definite_under_autograd():
+    """Forward-only: raised by mahal_and_det itself.  Under autograd the report is read asynchronously and raised by
+    backward() (cyclic_reduction.EAGER_PD_CHECK = True restores the eager check)."""
+    c = cr()
+    R, O, x = (t.cuda() for t in leg_inputs(3, 200, torch.float64, seed=9))
+    R[77] = -R[77]
+    with pytest.raises(c.NotPositiveDefiniteError):
+        c.mahal_and_det(R, O, x)
+    Rr = R.clone().requires_grad_(True)
+    mm, dd = c.mahal_and_det(Rr, O, x)
+    with pytest.raises(c.NotPositiveDefiniteError):
+        (mm + dd).backward()
+    c.EAGER_PD_CHECK = True
+    try:
+        with pytest.raises(c.NotPositiveDefiniteError):
+            c.mahal_and_det(R.clone().requires_grad_(True), O, x)
+    finally:
+        c.EAGER_PD_CHECK = False
