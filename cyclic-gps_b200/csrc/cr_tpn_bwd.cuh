@@ -223,17 +223,23 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
     for (int c = 0; c < L; ++c) {
       // column c of the inverse, top to bottom; the recurrence for column c reads K[r][k] with k >= c only,
       // and column c is replaced after its own recurrence, so later columns still see K where they need it
+      // (all loops run over the full constant range with compile-time guards: with triangular bounds the
+      // compiler left them rolled for ell = 5, 6 and put the matrix into local memory)
       T col[L];
-      col[c] = dinv[c];
 #pragma unroll
-      for (int r = c + 1; r < L; ++r) {
-        T s = T(0);
+      for (int r = 0; r < L; ++r) {
+        if (r == c) col[r] = dinv[c];
+        if (r > c) {
+          T s = T(0);
 #pragma unroll
-        for (int k = c; k < r; ++k) s = fma(Mx[r][k], col[k], s);
-        col[r] = -s * dinv[r];
+          for (int k = 0; k < L; ++k)
+            if (k >= c && k < r) s = fma(Mx[r][k], col[k], s);
+          col[r] = -s * dinv[r];
+        }
       }
 #pragma unroll
-      for (int r = c; r < L; ++r) Mx[r][c] = col[r];
+      for (int r = 0; r < L; ++r)
+        if (r >= c) Mx[r][c] = col[r];
     }
 #pragma unroll
     for (int c = 0; c < L; ++c) dxs[c] = T(0);
