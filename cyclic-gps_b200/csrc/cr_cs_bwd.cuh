@@ -37,7 +37,7 @@ struct CsBwdCfg {
   using Rec = CsBwdRec<T, L>;
   static constexpr int NS = Rec::NS;
   static constexpr size_t SMEM = (size_t)(NT + 1) * NS * sizeof(T);
-  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
+  static constexpr int MIN_CTAS = cmin(CRB200_CS_MAX_CTAS, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
 };
 
 // slice of CW consecutive elements (16-byte multiple) from / to shared memory

@@ -33,7 +33,7 @@ struct CsFwdCfg {
   using Rec = CsFwdRec<T, L>;
   static constexpr int NS = Rec::NS;
   static constexpr size_t SMEM = (size_t)NT * NS * sizeof(T);
-  static constexpr int MIN_CTAS = cmin(16, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
+  static constexpr int MIN_CTAS = cmin(CRB200_CS_MAX_CTAS, cmax(1, (int)((226 * 1024) / (SMEM + 1024))));
 };
 
 template <typename T, int L, int LPN>

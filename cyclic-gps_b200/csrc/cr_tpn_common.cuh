@@ -11,6 +11,10 @@
 #ifndef CRB200_SMEM_PAD
 #define CRB200_SMEM_PAD 0      // extra dynamic shared memory per CTA (lowers the CTAs/SM; profiling experiments)
 #endif
+#ifndef CRB200_CS_MAX_CTAS
+#define CRB200_CS_MAX_CTAS 8   // cap of the resident-CTA hint of the column-split kernels: at 9-10 CTAs ptxas limits the fp64 ell = 8
+                               // kernels to 168 registers and spills ~200 B; at 8 they get 224 / 242 registers, no spills (+1 %)
+#endif
 #ifndef CRB200_TPN_WARPS
 #define CRB200_TPN_WARPS 1     // independent single-tile warps per CTA of the thread-per-node kernels
 #endif
