@@ -79,9 +79,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, busy=None):
+        """`busy`: callable that keeps the GPU under the benchmark's load; nvidia-smi needs a few hundred ms to
+        deliver its first line, so short runs repeat the workload until at least two samples exist (<= 3 s)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = time.perf_counter()
+        while busy is not None and len(self.lines) < 2 and time.perf_counter() - t0 < 3.0:
+            busy()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -265,7 +270,10 @@ def run_long(args):
         step()
     sync()
     trace.enabled = False
-    clk = clocks.stop() if rank == 0 else None
+    def _busy():
+        step()
+        torch.cuda.synchronize()
+    clk = clocks.stop(busy=_busy if world == 1 else None) if rank == 0 else None   # (extra steps on one rank only would hang a collective)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -425,7 +433,10 @@ def main():
         step()
     sync()
     trace.enabled = False
-    clk = clocks.stop() if rank == 0 else None
+    def _busy():
+        step()
+        torch.cuda.synchronize()
+    clk = clocks.stop(busy=_busy if world == 1 else None) if rank == 0 else None   # (extra steps on one rank only would hang a collective)
     launches_per_step = len(trace.records) // max(args.steps, 1)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
