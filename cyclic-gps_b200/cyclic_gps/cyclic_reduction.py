@@ -259,14 +259,58 @@ def backhalfsolve(decomp, ycrr):
     return _to_caller(w, batched, ycrr[0].device)
 
 
-def solve(decomp, y):
-    """J^{-1} y  (reference :441-444)."""
-    pack, batched, caller = _pack_of(decomp)
-    dev = _engine.require_cuda()
-    Y = _batched(_dev(y, dev, pack.dtype), batched)
+def _solve_on_device(pack, Y):
     (X_flat, X), _ = _engine.halfsolve_sweep(pack, Y)
     _, _, w = _engine.backward_sweep(pack, sigma=False, w=True, xs=X, xs_flat=X_flat)
-    return _to_caller(w, batched, y.device)
+    return w
+
+
+class _SolveFn(torch.autograd.Function):
+    """w = J^{-1} y, differentiable wrt y and wrt the (Rs, Os) that were handed to ``decompose`` (the
+    reference's callers detach the solve, reference autograd through ``solve(decompose(Rs, Os), y)`` is the oracle).
+    With u = J^{-1} g (one more pair of sweeps against the same factors):
+        gy = u,   gR_i = -(u_i w_i^T + w_i u_i^T) / 2,   gO_i = -(u_{i+1} w_i^T + w_{i+1} u_i^T)
+    (the diagonal-block gradient is symmetric, as torch's Cholesky backward makes it)."""
+
+    @staticmethod
+    def forward(ctx, Rs, Os, y, decomp):
+        pack, batched, _ = _pack_of(decomp)
+        dev = _engine.require_cuda()
+        Y = _batched(_dev(y, dev, pack.dtype), batched)
+        w = _solve_on_device(pack, Y)
+        ctx.pack, ctx.batched, ctx.w = pack, batched, w
+        ctx.devs = (Rs.device if Rs is not None else None, Os.device if Os is not None else None, y.device)
+        return _to_caller(w, batched, y.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        pack, batched, w = ctx.pack, ctx.batched, ctx.w
+        dev = pack.device
+        u = _solve_on_device(pack, _batched(_dev(g, dev, pack.dtype), batched))
+        gR = gO = None
+        if ctx.needs_input_grad[0]:
+            uw = u.unsqueeze(-1) * w.unsqueeze(-2)
+            gR = _to_caller(-0.5 * (uw + uw.transpose(-1, -2)), batched, ctx.devs[0])
+        if ctx.needs_input_grad[1]:
+            gO = -(u[:, 1:].unsqueeze(-1) * w[:, :-1].unsqueeze(-2) + w[:, 1:].unsqueeze(-1) * u[:, :-1].unsqueeze(-2))
+            gO = _to_caller(gO, batched, ctx.devs[1])
+        gy = _to_caller(u, batched, ctx.devs[2]) if ctx.needs_input_grad[2] else None
+        return gR, gO, gy, None
+
+
+def solve(decomp, y):
+    """J^{-1} y  (reference :441-444).  Differentiable wrt ``y`` and, for a decomposition made by this module's
+    ``decompose``, wrt its ``Rs`` / ``Os``."""
+    pack, batched, caller = _pack_of(decomp)
+    Rs = decomp._Rs if isinstance(decomp, CRDecomp) else None
+    Os = decomp._Os if isinstance(decomp, CRDecomp) else None
+    needs = torch.is_grad_enabled() and (y.requires_grad or any(t is not None and t.requires_grad for t in (Rs, Os)))
+    if needs:
+        return _SolveFn.apply(Rs, Os, y, decomp)
+    dev = _engine.require_cuda()
+    Y = _batched(_dev(y, dev, pack.dtype), batched)
+    return _to_caller(_solve_on_device(pack, Y), batched, y.device)
 
 
 def mahal(decomp, y):

@@ -382,3 +382,23 @@ def test_not_positive_definite_under_autograd():
             c.mahal_and_det(R.clone().requires_grad_(True), O, x)
     finally:
         c.EAGER_PD_CHECK = False
+
+
+@pytest.mark.parametrize("l,n,dtype", [(3, 257, torch.float64), (8, 500, torch.float64), (4, 333, torch.float32)])
+def test_solve_is_differentiable(l, n, dtype):
+    """Gradient of a scalar function of solve(decompose(Rs, Os), y) wrt y, Rs, Os against torch autograd through the
+    oracle (the reference's own autograd path for the same expression)."""
+    c = cr()
+    R, O, x = leg_inputs(l, n, dtype, seed=5 * l + n)
+    coef = torch.randn((n, l), generator=torch.Generator().manual_seed(7), dtype=torch.float64)
+    Rg, Og, xg = (t.cuda().requires_grad_(True) for t in (R, O, x))
+    w = c.solve(c.decompose(Rg, Og), xg)
+    (w * coef.to(dtype).cuda()).sum().backward()
+    Ro, Oo, xo = (t.double().requires_grad_(True) for t in (R, O, x))
+    wo = orc.solve(orc.factor(Ro, Oo), xo)
+    (wo * coef).sum().backward()
+    tol = TOL[dtype]
+    assert_close(w, wo, tol, "solve")
+    assert_close(xg.grad, xo.grad, tol, "d/dy")
+    assert_close(Rg.grad, Ro.grad, tol, "d/dRs")
+    assert_close(Og.grad, Oo.grad, tol, "d/dOs")
