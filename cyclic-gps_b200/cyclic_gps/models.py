@@ -105,15 +105,17 @@ class LEGFamily(_Base):
 
     # ---- precision blocks (reference models.py:181-239, 254-280)
     def compute_PEG_precision(self, ts):
-        """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision."""
-        gaps = ts[1:] - ts[:-1]
+        """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision; a leading batch axis of
+        independent series, ts (B,n), gives (B,n,l,l) and (B,n-1,l,l) (the reference is batch-of-one)."""
+        gaps = ts[..., 1:] - ts[..., :-1]
         eye = torch.eye(self.rank, dtype=self.G.dtype, device=self.G.device)
-        A = torch.matrix_exp(-0.5 * self.G.unsqueeze(0) * gaps.reshape(-1, 1, 1))
-        At = A.transpose(1, 2)
+        A = torch.matrix_exp(-0.5 * self.G * gaps.unsqueeze(-1).unsqueeze(-1))
+        At = A.transpose(-1, -2)
         fwd = torch.linalg.solve(eye - A @ At, A)            # (I - A A^T)^{-1} A
         bwd = torch.linalg.solve(eye - At @ A, At)           # (I - A^T A)^{-1} A^T
         from_prev, to_next = A @ bwd, At @ fwd
-        diag = torch.cat([(eye + to_next[0]).unsqueeze(0), eye + from_prev[:-1] + to_next[1:], (eye + from_prev[-1]).unsqueeze(0)], dim=0)
+        diag = torch.cat([(eye + to_next[..., :1, :, :]), eye + from_prev[..., :-1, :, :] + to_next[..., 1:, :, :],
+                          (eye + from_prev[..., -1:, :, :])], dim=-3)
         return diag, -fwd
 
     def _obs_terms(self):
@@ -123,11 +125,11 @@ class LEGFamily(_Base):
     def compute_posterior_precision(self, ts):
         _, shift = self._obs_terms()
         Rs, Os = self.compute_PEG_precision(ts)
-        return Rs + shift.unsqueeze(0), Os
+        return Rs + shift, Os
 
     def compute_v(self, xs):
         LLT = self.calc_Lambda_Lambda_T(self.Lambda)
-        return torch.linalg.solve(LLT, xs.T).T @ self.B
+        return torch.linalg.solve(LLT, xs.transpose(-1, -2)).transpose(-1, -2) @ self.B
 
     def compute_insample_posterior(self, ts, xs):
         """Posterior mean (n,l) and {"Rs","Os"} blocks of the posterior covariance
@@ -141,16 +143,18 @@ class LEGFamily(_Base):
         return mean, cov
 
     def log_likelihood(self, ts, xs):
-        """log p(xs | ts) through two CR factorisations (reference models.py:301-372)."""
+        """log p(xs | ts) through two CR factorisations (reference models.py:301-372).  ts (n,), xs (n,d) give a
+        scalar as in the reference; a batch of independent series, ts (B,n) and xs (B,n,d), gives (B,) values from
+        ONE batched pass of the CR engine (the series share the model parameters)."""
         self.register_model_matrices_from_params()
         LLT, shift = self._obs_terms()
-        white = torch.linalg.solve(LLT, xs.T).T
-        obs_mahal = torch.sum(white * xs)
-        obs_logdet = torch.logdet(2 * math.pi * LLT) * xs.shape[0]
+        white = torch.linalg.solve(LLT, xs.transpose(-1, -2)).transpose(-1, -2)
+        obs_mahal = torch.sum(white * xs, dim=(-1, -2))
+        obs_logdet = torch.logdet(2 * math.pi * LLT) * xs.shape[-2]
         v = white @ self.B
         Rs, Os = self.compute_PEG_precision(ts)
         prior_logdet = det(decompose(Rs, Os))
-        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift.unsqueeze(0), Os=Os, x=v)
+        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift, Os=Os, x=v)
         return -0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))
 
     # ---- training hooks (reference models.py:374-392)

@@ -117,3 +117,29 @@ def test_co2_shaped_training_step():
         sd, so = orc.selected_inverse(dec)
         assert_close(cov["Rs"], sd, 1e-9, "posterior cov diag")
         assert_close(cov["Os"], so, 1e-9, "posterior cov off")
+
+
+def test_batched_log_likelihood_equals_loop():
+    """LEGFamily.log_likelihood with a leading batch axis (ts (B,n), xs (B,n,d)): values and parameter gradients
+    must equal the loop over single series (the reference's batch-of-one semantics)."""
+    from cyclic_gps.models import LEGFamily
+    torch.manual_seed(3)
+    B, n, rank, d = 4, 300, 5, 2
+    model = LEGFamily(rank=rank, obs_dim=d, train=True, data_type=torch.float64).cuda()
+    ts = torch.cumsum(torch.rand(B, n, dtype=torch.float64, device="cuda") + 0.05, dim=1)
+    xs = torch.randn(B, n, d, dtype=torch.float64, device="cuda")
+    wts = torch.tensor([0.5, 1.0, 1.5, 2.0], dtype=torch.float64, device="cuda")
+    ll_b = model.log_likelihood(ts=ts, xs=xs)
+    assert ll_b.shape == (B,)
+    (ll_b * wts).sum().backward()
+    grads_b = [p.grad.clone() for p in model.parameters()]
+    for p in model.parameters():
+        p.grad = None
+    total = 0
+    for b in range(B):
+        ll = model.log_likelihood(ts=ts[b], xs=xs[b])
+        assert abs(float(ll.detach()) - float(ll_b[b].detach())) <= 1e-10 * abs(float(ll.detach()))
+        total = total + wts[b] * ll
+    total.backward()
+    for g_b, p in zip(grads_b, model.parameters()):
+        assert float((g_b - p.grad).abs().max()) <= 1e-9 * max(float(p.grad.abs().max()), 1e-30)
