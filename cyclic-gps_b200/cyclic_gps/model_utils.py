@@ -27,6 +27,17 @@ def build_3x3_block(a, b, c, d, e, f, g, h, i):
     return torch.cat([torch.cat([a, b, c], dim=-1), torch.cat([d, e, f], dim=-1), torch.cat([g, h, i], dim=-1)], dim=-2)
 
 
+def gaussian_stitch(joint_mean, joint_cov, marginal_mean, marginal_cov):
+    """Mean and covariance of y under q(x, y) = p2(x) p1(y | x), with p1 = N(joint_mean, joint_cov) over (x, y) and
+    p2 = N(marginal_mean, marginal_cov) over x (reference model_utils.py:64-107; the reference's formula, which
+    assumes a zero joint mean for the x part).  Batched over leading axes."""
+    m = marginal_cov.shape[-1]
+    T = joint_cov[..., m:, :m] @ torch.linalg.inv(joint_cov[..., :m, :m])
+    mean = joint_mean[..., m:] + (T @ marginal_mean.unsqueeze(-1)).squeeze(-1)
+    cond = joint_cov[..., m:, m:] - T @ joint_cov[..., :m, m:]
+    return mean, cond + T @ marginal_cov @ T.transpose(-1, -2)
+
+
 def compute_prior_covariance(ts, G):
     """Dense stationary LEG prior covariance, block (i,j) = exp(-|t_i - t_j|/2 G) for i > j and its
     transpose above the diagonal (reference model_utils.py:110-128, vectorised over all pairs)."""

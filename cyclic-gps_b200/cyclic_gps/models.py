@@ -2,8 +2,9 @@
 to what calls the CR hot path: parameters -> G -> block-tridiagonal precision (Rs, Os) ->
 ``decompose`` / ``det`` / ``mahal_and_det`` / ``solve`` / ``inverse_blocks`` from
 ``cyclic_gps.cyclic_reduction`` (the B200 engine).  The prediction helpers of the reference
-(forecast / interpolate / intercast / make_predictions, models.py:394-546) are outside the
-hot path and not provided.  ``pytorch_lightning`` is optional: without it the class is a plain
+(forecast / interpolate / intercast / predictive_posterior / make_predictions, models.py:394-546) are plain torch
+glue behind the in-sample posterior, vectorised over the targets (the reference loops over them in Python).
+``pytorch_lightning`` is optional: without it the class is a plain
 ``torch.nn.Module`` with the same training_step / configure_optimizers hooks."""
 import math
 
@@ -12,6 +13,7 @@ from torch.optim import LBFGS, Adam
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_and_det, solve
+from cyclic_gps.model_utils import build_2x2_block, build_3x3_block, compute_eG, gaussian_stitch
 
 try:  # pragma: no cover - not installed in the build image
     import pytorch_lightning as pl
@@ -156,6 +158,69 @@ class LEGFamily(_Base):
         prior_logdet = det(decompose(Rs, Os))
         K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift, Os=Os, x=v)
         return -0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))
+
+    # ---- predictions at new times (reference models.py:394-546), vectorised over the targets
+    def forecast(self, eG, ip_mean, ip_cov):
+        """Latent mean / covariance one gap away from an in-sample time; eG = exp(-gap/2 G) (transposed by the
+        caller when looking backwards), reference models.py:394-407."""
+        eye = torch.eye(self.rank, dtype=eG.dtype, device=eG.device).expand_as(eG)
+        joint_cov = build_2x2_block(eye, eG.transpose(-1, -2), eG, eye)
+        joint_mean = torch.zeros(eG.shape[:-2] + (2 * self.rank,), dtype=eG.dtype, device=eG.device)
+        return gaussian_stitch(joint_mean, joint_cov, ip_mean, ip_cov)
+
+    def interpolate(self, eG1, eG2, prev_ip_mean, prev_ip_cov_diag, prev_ip_cov_offdiag, next_ip_mean, next_ip_cov_diag):
+        """Latent mean / covariance between two in-sample times (reference models.py:409-451)."""
+        eye = torch.eye(self.rank, dtype=eG1.dtype, device=eG1.device).expand_as(eG1)
+        eG3 = eG1 @ eG2
+        t = lambda a: a.transpose(-1, -2)
+        joint_cov = build_3x3_block(eye, t(eG3), t(eG1), eG3, eye, eG2, eG1, t(eG2), eye)
+        joint_mean = torch.zeros(eG1.shape[:-2] + (3 * self.rank,), dtype=eG1.dtype, device=eG1.device)
+        ip_mean = torch.cat([prev_ip_mean, next_ip_mean], dim=-1)
+        ip_cov = build_2x2_block(prev_ip_cov_diag, t(prev_ip_cov_offdiag), prev_ip_cov_offdiag, next_ip_cov_diag)
+        return gaussian_stitch(joint_mean, joint_cov, ip_mean, ip_cov)
+
+    def intercast(self, ip_mean, ip_cov, ts, target_ts, thresh=1e-10):
+        """Posterior of the latent process at `target_ts` (sorted) from the in-sample posterior
+        (reference models.py:454-515: forecast before / after the data, interpolate inside, exact hits at the ends)."""
+        assert bool((target_ts[1:] - target_ts[:-1] > 0).all())
+        dev, dt = ip_mean.device, ip_mean.dtype
+        ts, target_ts = ts.to(dev), target_ts.to(dev)
+        G_val, G_vec = torch.linalg.eig(self.G.detach().cpu())         # G is tiny; one eigendecomposition on the host
+        G_vec_inv = torch.linalg.inv(G_vec)
+        G_val, G_vec, G_vec_inv = G_val.to(dev), G_vec.to(dev), G_vec_inv.to(dev)
+        eG = lambda gaps: compute_eG(G_val, G_vec, G_vec_inv, gaps).to(dt)
+        n = ts.shape[0]
+        Rs, Os = ip_cov["Rs"], ip_cov["Os"]
+        idx = torch.searchsorted(ts, target_ts)
+        close = lambda a, b: (a - b).abs() <= 1e-8 + 1e-5 * b.abs()     # torch.allclose defaults
+        before, after = idx == 0, idx == n
+        at_first, at_last = before & close(target_ts, ts[0]), close(target_ts, ts[-1])
+        # forecasting backwards from the first / forwards from the last in-sample time
+        mb, vb = self.forecast(eG((ts[0] - target_ts).clamp(min=0)).transpose(-1, -2), ip_mean[0], Rs[0])
+        ma, va = self.forecast(eG((target_ts - ts[-1]).clamp(min=0)), ip_mean[-1], Rs[-1])
+        # interpolation between ts[idx-1] and ts[idx]
+        lo, hi = (idx - 1).clamp(0, n - 2), idx.clamp(1, n - 1)
+        mi, vi = self.interpolate(eG((target_ts - ts[lo]).clamp(min=0)), eG((ts[hi] - target_ts).clamp(min=0)),
+                                  ip_mean[lo], Rs[lo], Os[lo], ip_mean[hi], Rs[hi])
+        pick = lambda c, a, b: torch.where(c.reshape((-1,) + (1,) * (a.dim() - 1)), a, b)
+        mean, cov = pick(before, mb, pick(after, ma, mi)), pick(before, vb, pick(after, va, vi))
+        mean, cov = pick(at_first, ip_mean[0].expand_as(mean), mean), pick(at_first, Rs[0].expand_as(cov), cov)
+        exact_last = at_last & ~before
+        mean, cov = pick(exact_last, ip_mean[-1].expand_as(mean), mean), pick(exact_last, Rs[-1].expand_as(cov), cov)
+        return mean, cov
+
+    def predictive_posterior(self, ts, xs, target_ts):
+        """E[z(t) | xs], Cov[z(t) | xs] at the target times (reference models.py:517-530)."""
+        mean, cov = self.compute_insample_posterior(ts, xs)
+        return self.intercast(mean, cov, ts, target_ts)
+
+    def make_predictions(self, ts, xs, target_ts):
+        """Predicted observations: means (m, obs_dim) and covariances (m, obs_dim, obs_dim) at the target times,
+        without the observation noise (reference models.py:532-546)."""
+        self.calc_G()
+        zm, zv = self.predictive_posterior(ts, xs, target_ts)
+        B = self.B.to(zm.device)
+        return zm @ B.T, B.unsqueeze(0) @ zv @ B.T.unsqueeze(0)
 
     # ---- training hooks (reference models.py:374-392)
     def training_step(self, train_batch, batch_idx):

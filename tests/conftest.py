@@ -34,4 +34,4 @@ def golden():
 
     d = os.path.join(ROOT, "tests", "golden")
     return {name: np.load(os.path.join(d, name + ".npz"), allow_pickle=False)
-            for name in ("random_llt", "known", "leg", "helpers", "leg_model")}
+            for name in ("random_llt", "known", "leg", "helpers", "leg_model", "predictions")}

@@ -17,6 +17,7 @@ stored is numeric input/output data of the reference's own functions:
                      factors and reference-autograd gradients
   helpers.npz        UU_T / Ux / U_Tx / SigU / UtV_diags / interleave
   leg_model.npz      LEGFamily.log_likelihood / compute_insample_posterior values
+  predictions.npz    LEGFamily.predictive_posterior / make_predictions values (models.py:394-546)
 """
 import os
 import sys
@@ -279,12 +280,48 @@ def gen_leg_model():
     np.savez_compressed(os.path.join(HERE, "leg_model.npz"), **out)
 
 
+def gen_predictions():
+    """LEGFamily.make_predictions / predictive_posterior of the reference (models.py:394-546): targets before the
+    first observation, at the first, between observations, AT an inner observation time, at the last and beyond it."""
+    out = {}
+    cases = []
+    torch.manual_seed(23)
+    for spacing in ("regular", "irregular"):
+        for (n, d, rank) in ((12, 1, 3), (40, 2, 5)):
+            g = torch.Generator().manual_seed(7 * n + d)
+            if spacing == "regular":
+                ts = torch.arange(n, dtype=torch.float64)
+            else:
+                ts = torch.cumsum(-torch.log(torch.rand(n, generator=g, dtype=torch.float64)) + 0.05, 0)
+            xs = torch.randn((n, d), generator=g, dtype=torch.float64)
+            inner = ts[:-1] + (ts[1:] - ts[:-1]) * torch.rand(n - 1, generator=g, dtype=torch.float64)
+            target = torch.cat([ts[:1] - 2.5, ts[:1] - 0.3, ts[:1], inner[::3], ts[n // 2:n // 2 + 1], ts[-1:], ts[-1:] + 0.4, ts[-1:] + 3.0])
+            target = torch.sort(torch.unique(target))[0]
+            model = LEGFamily(rank=rank, obs_dim=d, train=False, data_type=torch.float64)
+            model.double()
+            p = f"{spacing}_n{n}_d{d}_r{rank}_"
+            out[p + "ts"], out[p + "xs"], out[p + "target"] = npy(ts), npy(xs), npy(target)
+            for name in ("N_params", "R_params", "Lambda_params", "B"):
+                out[p + name] = npy(getattr(model, name))
+            with torch.no_grad():
+                zm, zv = model.predictive_posterior(ts, xs, target)
+                xm, xv = model.make_predictions(ts, xs, target)
+            out[p + "z_mean"], out[p + "z_cov"], out[p + "x_mean"], out[p + "x_cov"] = npy(zm), npy(zv), npy(xm), npy(xv)
+            cases.append(p)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "predictions.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--predictions-only" in sys.argv:      # added after the other files were frozen
+        gen_predictions()
+        sys.exit(0)
     gen_random_llt()
     gen_known()
     gen_leg()
     gen_helpers()
     gen_leg_model()
+    gen_predictions()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

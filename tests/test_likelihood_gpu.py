@@ -143,3 +143,26 @@ def test_batched_log_likelihood_equals_loop():
     total.backward()
     for g_b, p in zip(grads_b, model.parameters()):
         assert float((g_b - p.grad).abs().max()) <= 1e-9 * max(float(p.grad.abs().max()), 1e-30)
+
+
+def test_predictions_match_the_reference(golden):
+    """LEGFamily.predictive_posterior / make_predictions (vectorised over targets here, a Python loop in the
+    reference, models.py:454-546) against golden vectors of the unmodified reference: targets before, at, between and
+    beyond the observation times."""
+    from cyclic_gps.models import LEGFamily
+    g = golden["predictions"]
+    for p in [str(c) for c in g["cases"]]:
+        ts, xs, target = (torch.from_numpy(g[p + k]).cuda() for k in ("ts", "xs", "target"))
+        rank = int(p.split("_r")[-1].rstrip("_"))
+        m = LEGFamily(rank=rank, obs_dim=xs.shape[-1], train=False, data_type=torch.float64)
+        for name in ("N_params", "R_params", "Lambda_params", "B"):
+            getattr(m, name).data = torch.from_numpy(g[p + name])
+        m.register_model_matrices_from_params()
+        m = m.cuda()
+        with torch.no_grad():
+            zm, zv = m.predictive_posterior(ts, xs, target)
+            xm, xv = m.make_predictions(ts, xs, target)
+        for ours, key in ((zm, "z_mean"), (zv, "z_cov"), (xm, "x_mean"), (xv, "x_cov")):
+            ref = torch.from_numpy(g[p + key])
+            err = float((ours.cpu() - ref).abs().max() / ref.abs().max())
+            assert err < 1e-8, (p, key, err)

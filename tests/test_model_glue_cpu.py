@@ -59,3 +59,29 @@ def test_generate_data_shapes():
     assert ts.shape == (20,) and xs.shape == (20, 3) and bool((ts[1:] > ts[:-1]).all())
     ds = time_series_dataset(ts.unsqueeze(0), xs.unsqueeze(0))
     assert len(ds) == 1 and ds[0][0].shape == (20,)
+
+
+def test_intercast_vectorised_matches_reference_loop(golden):
+    """The vectorised forecast / interpolate / intercast glue (torch only) against golden vectors of the reference's
+    per-target Python loop (models.py:454-515); the in-sample posterior comes from the CPU oracle here, the GPU test
+    tests/test_likelihood_gpu.py::test_predictions_match_the_reference runs the whole path through the CUDA engine."""
+    import torch
+    from cyclic_gps.models import LEGFamily
+    from oracle import cr_oracle as orc
+    g = golden["predictions"]
+    for p in [str(c) for c in g["cases"]]:
+        ts, xs, target = (torch.from_numpy(g[p + k]) for k in ("ts", "xs", "target"))
+        rank = int(p.split("_r")[-1].rstrip("_"))
+        m = LEGFamily(rank=rank, obs_dim=xs.shape[-1], train=False, data_type=torch.float64)
+        for name in ("N_params", "R_params", "Lambda_params", "B"):
+            getattr(m, name).data = torch.from_numpy(g[p + name])
+        m.register_model_matrices_from_params()
+        with torch.no_grad():
+            Rs, Os = m.compute_posterior_precision(ts)
+            dec = orc.factor(Rs, Os)
+            mean = orc.solve(dec, m.compute_v(xs))
+            sd, so = orc.selected_inverse(dec)
+            zm, zv = m.intercast(mean, {"Rs": sd, "Os": so}, ts, target)
+        for ours, key in ((zm, "z_mean"), (zv, "z_cov")):
+            ref = torch.from_numpy(g[p + key])
+            assert float((ours - ref).abs().max() / ref.abs().max()) < 1e-10, (p, key)
