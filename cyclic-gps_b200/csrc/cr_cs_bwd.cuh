@@ -25,7 +25,7 @@ struct CsBwdRec {
   static constexpr int BS = L * L;
   static constexpr int A = 0, SD = BS, C = 2 * BS, B = 3 * BS, SO = 4 * BS, X = 5 * BS, WT = 5 * BS + L;
   static constexpr int RAW = 5 * BS + 2 * L;
-  static constexpr int NS = record_stride<T>(RAW);
+  static constexpr int NS = record_stride<T>(RAW, BS);
 };
 
 template <typename T, int L, int LPN>

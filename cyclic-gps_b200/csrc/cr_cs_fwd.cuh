@@ -21,7 +21,7 @@ struct CsFwdRec {
   static constexpr int BS = L * L;
   static constexpr int RE = 0, RO = BS, OL = 2 * BS, OR_ = 3 * BS, ON = 4 * BS, YE = 5 * BS, YO = 5 * BS + L;
   static constexpr int RAW = 5 * BS + 2 * L;
-  static constexpr int NS = record_stride<T>(RAW);
+  static constexpr int NS = record_stride<T>(RAW, BS);
 };
 
 template <typename T, int L, int LPN>

@@ -37,12 +37,12 @@ struct TpnBwdCfg {
   // 8 CTAs on an SM (fp32 ell = 7, 8; fp64 ell = 5); otherwise S~_d and S~_o get slots of their own, everything is
   // requested up front and Sigma_{2e,2e} leaves through the A slot (measured: at ell = 4 fp32, 17 CTAs/SM with five
   // blocks beat 26 CTAs/SM with three blocks and three dependent load phases, 5.34 vs 6.03 ms on the long series)
-  static constexpr int CTAS5 = (int)((228 * 1024) / ((size_t)(NT + 1) * record_stride<T>(5 * BS + 2 * L) * sizeof(T) + 1024));
+  static constexpr int CTAS5 = (int)((228 * 1024) / ((size_t)(NT + 1) * record_stride<T>(5 * BS + 2 * L, BS) * sizeof(T) + 1024));
   static constexpr bool COMPACT = CTAS5 < 8;
   static constexpr int A = 0, SD = COMPACT ? 0 : BS, C = COMPACT ? BS : 2 * BS, B = C + BS, SO = COMPACT ? B : 4 * BS;
   static constexpr int X = (COMPACT ? 3 : 5) * BS, WT = X + L;
   static constexpr int RAW = X + 2 * L;
-  static constexpr int NS = record_stride<T>(RAW);
+  static constexpr int NS = record_stride<T>(RAW, BS);
   static constexpr size_t SMEM_W = (size_t)(NT + 1) * NS * sizeof(T);           // per warp
   static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
   static constexpr size_t SMEM = SMEM_W * NW + CRB200_SMEM_PAD;   // CRB200_SMEM_PAD: occupancy experiments only

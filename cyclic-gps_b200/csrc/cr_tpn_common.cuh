@@ -24,6 +24,38 @@ namespace crb200 {
 __device__ __forceinline__ void cp_async16_u32(unsigned saddr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem) : "memory");
 }
+template <typename T>
+__device__ __forceinline__ void cp_async_elem_u32(unsigned saddr, const T* gmem) {
+  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gmem) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gmem) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ T lds_elem_u32(unsigned saddr) {
+  T v;
+  if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(saddr));
+  else asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(saddr));
+  return v;
+}
+// Element-by-element walk over records (blocks that are not a multiple of 16 bytes): lane starts at element
+// k0 = lane + first, every step advances 32 elements; (record, offset) are carried along instead of being
+// recomputed with a division per element (that arithmetic cost as much as the block algebra at ell = 7).
+template <int EPR>
+struct ElemWalk {
+  static constexpr unsigned SR = 32 / EPR, SC = 32 % EPR;
+  unsigned c, saddr;
+  __device__ __forceinline__ ElemWalk(unsigned srec0, unsigned nsb, unsigned es, unsigned first) {
+    const unsigned k0 = (threadIdx.x & 31) + first;
+    const unsigned rec = k0 / EPR;
+    c = k0 - rec * EPR;
+    saddr = srec0 + rec * nsb + c * es;
+  }
+  __device__ __forceinline__ void next(unsigned nsb, unsigned es) {
+    c += SC;
+    saddr += SR * nsb + SC * es;
+    if (c >= EPR) { c -= EPR; saddr += nsb - EPR * es; }
+  }
+};
+
 __device__ __forceinline__ int4 lds128_u32(unsigned saddr) {
   int4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -75,12 +107,9 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
   }
   constexpr int EPR = UE * GRP;
   const int total = nunits * UE;
-  for (int i = lane; i < total; i += 32) {
-    const unsigned k = (unsigned)(i + kstart * UE);
-    const unsigned rec = k / EPR, c = k - rec * EPR;
-    T* dst = reinterpret_cast<T*>(__cvta_shared_to_generic(srec0 + rec * nsb)) + c;
-    cp_async_elem(dst, g + i);
-  }
+  ElemWalk<EPR> w(srec0, nsb, (unsigned)sizeof(T), (unsigned)(kstart * UE));
+  const T* gp = g + lane;
+  for (int i = lane; i < total; i += 32, gp += 32, w.next(nsb, (unsigned)sizeof(T))) cp_async_elem_u32<T>(w.saddr, gp);
 }
 
 // Every GS-th global unit -> one unit per record (unit j = global unit j * GS lands in record kstart + j).
@@ -110,11 +139,17 @@ __device__ __forceinline__ void rec_g2s_strided(unsigned srec0, unsigned nsb, co
       return;
     }
   }
+  // one unit per record: the global side skips (GS - 1) units whenever the walk moves to the next record
   const int total = nunits * UE;
+  ElemWalk<UE> w(srec0 + kstart * nsb, nsb, (unsigned)sizeof(T), 0u);
+  const unsigned j0 = (unsigned)lane / UE;
+  const T* gp = g + (size_t)j0 * GS * UE + ((unsigned)lane - j0 * UE);
+  constexpr unsigned SR = 32 / UE, SC = 32 % UE;
   for (int i = lane; i < total; i += 32) {
-    const unsigned j = (unsigned)i / UE, c = (unsigned)i - j * UE;
-    T* dst = reinterpret_cast<T*>(__cvta_shared_to_generic(srec0 + (kstart + j) * nsb)) + c;
-    cp_async_elem(dst, g + (size_t)j * GS * UE + c);
+    cp_async_elem_u32<T>(w.saddr, gp);
+    const unsigned cb = w.c;
+    w.next(nsb, (unsigned)sizeof(T));
+    gp += (size_t)SR * GS * UE + SC + ((cb + SC >= (unsigned)UE) ? (size_t)(GS - 1) * UE : 0);
   }
 }
 
@@ -175,11 +210,9 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
   }
   constexpr int EPR = UE * GRP;
   const int total = nunits * UE;
-  for (int i = lane; i < total; i += 32) {
-    const unsigned k = (unsigned)(i + kstart * UE);
-    const unsigned rec = k / EPR, c = k - rec * EPR;
-    g[i] = reinterpret_cast<const T*>(__cvta_shared_to_generic(srec0 + rec * nsb))[c];
-  }
+  ElemWalk<EPR> w(srec0, nsb, (unsigned)sizeof(T), (unsigned)(kstart * UE));
+  T* gp = g + lane;
+  for (int i = lane; i < total; i += 32, gp += 32, w.next(nsb, (unsigned)sizeof(T))) *gp = lds_elem_u32<T>(w.saddr);
 }
 
 // One unit per record -> every GS-th global unit (record kstart + j -> global unit j * GS): the mirror of
@@ -210,9 +243,15 @@ __device__ __forceinline__ void rec_s2g_strided(T* __restrict__ g, unsigned srec
     }
   }
   const int total = nunits * UE;
+  ElemWalk<UE> w(srec0 + kstart * nsb, nsb, (unsigned)sizeof(T), 0u);
+  const unsigned j0 = (unsigned)lane / UE;
+  T* gp = g + (size_t)j0 * GS * UE + ((unsigned)lane - j0 * UE);
+  constexpr unsigned SR = 32 / UE, SC = 32 % UE;
   for (int i = lane; i < total; i += 32) {
-    const unsigned j = (unsigned)i / UE, c = (unsigned)i - j * UE;
-    g[(size_t)j * GS * UE + c] = reinterpret_cast<const T*>(__cvta_shared_to_generic(srec0 + (kstart + j) * nsb))[c];
+    *gp = lds_elem_u32<T>(w.saddr);
+    const unsigned cb = w.c;
+    w.next(nsb, (unsigned)sizeof(T));
+    gp += (size_t)SR * GS * UE + SC + ((cb + SC >= (unsigned)UE) ? (size_t)(GS - 1) * UE : 0);
   }
 }
 
@@ -257,11 +296,16 @@ __device__ __forceinline__ void axpy_row(T (&acc)[L], T s, const T (&row)[L]) {
   }
 }
 
-// record stride (elements): payload rounded up to an ODD number of 16-byte chunks, so that the
-// 8 lanes of a quarter warp hit 8 different 16-byte bank groups on per-thread vector accesses
+// record stride (elements).  Blocks that are a multiple of 16 bytes are accessed with 16-byte vector loads / stores:
+// the payload is rounded up to an ODD number of 16-byte chunks, so that the 8 lanes of a quarter warp hit 8 different
+// 16-byte bank groups.  Other blocks (odd ell) are accessed element by element: an ODD number of ELEMENTS makes
+// the 32 lanes (fp32) / the 16 lanes of a half warp (fp64) hit distinct banks -- with the 16-byte rule those scalar
+// accesses were 4-way (fp32) / 2-way (fp64) bank conflicted (ell = 7 fp32 ran slower than ell = 8).
 template <typename T>
-__host__ __device__ constexpr int record_stride(int payload_elems) {
-  return ((((payload_elems * (int)sizeof(T)) + 15) / 16) | 1) * 16 / (int)sizeof(T);
+__host__ __device__ constexpr int record_stride(int payload_elems, int block_elems) {
+  return ((block_elems * (int)sizeof(T)) % 16 != 0)
+             ? (payload_elems | 1)
+             : ((((payload_elems * (int)sizeof(T)) + 15) / 16) | 1) * 16 / (int)sizeof(T);
 }
 
 }  // namespace crb200

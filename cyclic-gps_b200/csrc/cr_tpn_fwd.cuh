@@ -32,7 +32,7 @@ struct TpnFwdCfg {
   static constexpr int NT = 32, OWN = 31;
   static constexpr int RE = 0, OL = BS, OR_ = 2 * BS, YE = 3 * BS, YO = 3 * BS + L;   // RE: R_even, later R_odd -> R~
   static constexpr int RAW = 3 * BS + 2 * L;
-  static constexpr int NS = record_stride<T>(RAW);
+  static constexpr int NS = record_stride<T>(RAW, BS);
   static constexpr size_t SMEM_W = (size_t)NT * NS * sizeof(T);                 // per warp
   // independent warps per CTA (each warp = one tile): warps of a CTA run the same code at about the same time
   static constexpr int NW = cmax(1, cmin(CRB200_TPN_WARPS, (int)((220 * 1024) / (SMEM_W * 1 + 1024))));
