@@ -46,7 +46,9 @@ def bytes_per_row_total(ell, s):
 
 def kernel_family(ell, s):
     """Which kernel family libcrb200 dispatches to."""
-    return "tpn" if s * ell * ell <= 256 else "level"
+    if s * ell * ell <= 400:
+        return "tpn"                       # thread-per-node (CRB200_TPN_MAX_BLOCK_BYTES)
+    return "cs" if (s == 8 and ell == 8) else "level"
 
 
 def peaks():

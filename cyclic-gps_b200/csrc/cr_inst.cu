@@ -2,7 +2,7 @@
 // in parallel.  -DCRB_T=float|double -DCRB_TN=f32|f64 -DCRB_LO=.. -DCRB_HI=..
 #include "cr_level_fwd.cuh"
 #include "cr_level_bwd.cuh"
-#if CRB_LO <= 8   // thread-per-node kernels exist only where sizeof(T) * ell^2 <= 256 bytes
+#if CRB_LO <= 9   // thread-per-node kernels exist only for small blocks (CRB200_TPN_MAX_BLOCK_BYTES)
 #include "cr_tpn_fwd.cuh"
 #include "cr_tpn_bwd.cuh"
 #include "cr_cs_fwd.cuh"

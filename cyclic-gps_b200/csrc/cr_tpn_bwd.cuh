@@ -30,7 +30,7 @@ namespace crb200 {
 
 template <typename T, int L>
 struct TpnBwdCfg {
-  static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= 256);
+  static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= CRB200_TPN_MAX_BLOCK_BYTES);
   static constexpr int BS = L * L;
   static constexpr int NT = 32;
   // COMPACT (three blocks per node, A and B slots used twice) when five blocks per node would leave fewer than

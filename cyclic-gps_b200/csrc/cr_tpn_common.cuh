@@ -15,6 +15,11 @@
 #define CRB200_CS_MAX_CTAS 8   // cap of the resident-CTA hint of the column-split kernels: at 9-10 CTAs ptxas limits the fp64 ell = 8
                                // kernels to 168 registers and spills ~200 B; at 8 they get 224 / 242 registers, no spills (+1 %)
 #endif
+#ifndef CRB200_TPN_MAX_BLOCK_BYTES
+#define CRB200_TPN_MAX_BLOCK_BYTES 400   // largest block the thread-per-node kernels take: fp32 ell <= 10, fp64 ell <= 7.  Up to 324 B (fp32 ell = 9,
+                                          // fp64 ell = 6) P, Q and Sigma_ee fit in 254 registers; at 392-400 B the backward kernel spills ~0.5 KB and
+                                          // is still 1.2-1.5x faster than the lane-per-row kernels (profiles/r1_summary.md)
+#endif
 #ifndef CRB200_TPN_WARPS
 #define CRB200_TPN_WARPS 1     // independent single-tile warps per CTA of the thread-per-node kernels
 #endif

@@ -27,7 +27,7 @@ namespace crb200 {
 
 template <typename T, int L>
 struct TpnFwdCfg {
-  static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= 256);
+  static constexpr bool ELIGIBLE = (sizeof(T) * L * L <= CRB200_TPN_MAX_BLOCK_BYTES);
   static constexpr int BS = L * L;
   static constexpr int NT = 32, OWN = 31;
   static constexpr int RE = 0, OL = BS, OR_ = 2 * BS, YE = 3 * BS, YO = 3 * BS + L;   // RE: R_even, later R_odd -> R~

@@ -30,8 +30,8 @@ extern "C" {
 #define CRB200_F32 0
 #define CRB200_F64 1
 
-/* kernel families: lane-per-row (any ell <= 32), thread-per-node (sizeof(T)*ell*ell <= 256 B) and
- * column-split (several lanes per node: fp32 ell=8, fp64 ell=4 and 8) */
+/* kernel families: lane-per-row (any ell <= 32), thread-per-node (sizeof(T)*ell*ell <= 400 B: fp32 ell <= 10, fp64 ell <= 7) and
+ * column-split (several lanes per node: fp32 ell=8, fp64 ell=4 and 8; chosen automatically for fp64 ell=8) */
 #define CRB200_AUTO 0
 #define CRB200_LANE_PER_ROW 1
 #define CRB200_THREAD_PER_NODE 2

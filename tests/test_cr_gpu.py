@@ -175,7 +175,9 @@ def test_full_path_vs_oracle(l, n, dtype):
     (8, 777, torch.float64, 1), (8, 777, torch.float64, 3),
     (4, 1500, torch.float64, 1), (4, 1500, torch.float64, 2), (4, 1500, torch.float64, 3),
     (4, 3001, torch.float32, 1), (4, 3001, torch.float32, 2),
-    (3, 500, torch.float64, 1), (3, 500, torch.float64, 2), (5, 300, torch.float32, 1), (5, 300, torch.float32, 2)])
+    (3, 500, torch.float64, 1), (3, 500, torch.float64, 2), (5, 300, torch.float32, 1), (5, 300, torch.float32, 2),
+    (9, 700, torch.float32, 1), (9, 700, torch.float32, 2), (10, 700, torch.float32, 1), (10, 700, torch.float32, 2),   # upper end of thread-per-node
+    (6, 700, torch.float64, 1), (6, 700, torch.float64, 2), (7, 700, torch.float64, 1), (7, 700, torch.float64, 2)])
 def test_every_kernel_family_vs_oracle(l, n, dtype, variant):
     """The same contract is implemented by up to three kernel families (include/crb200.h, `variant`);
     force each one and compare the whole path (forward, backward, selected inverse, solve) with the oracle."""

@@ -19,7 +19,7 @@ def _cases():
     cases = []
     for i in range(44):
         n = rng.choice(edge_n) if i % 2 == 0 else rng.randint(1, 2600)
-        l = rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 8, 8, 4, 12, 16])
+        l = rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 8, 8, 4, 9, 10, 12, 16])
         dtype = rng.choice([torch.float32, torch.float64])
         batch = rng.choice([1, 1, 2, 5])
         cases.append((n, l, dtype, batch, i))

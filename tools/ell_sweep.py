@@ -4,7 +4,7 @@ usage: python tools/ell_sweep.py out.json"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = []
-cases = [(l, dt) for dt in ("float32", "float64") for l in (1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 24, 32)]
+cases = [(l, dt) for dt in ("float32", "float64") for l in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 24, 32)]
 for l, dt in cases:
     s = 4 if dt == "float32" else 8
     rows = int(min(5.12e6, 2.0e9 / (l * l * s)))            # keep inputs + factors around a few GB
