@@ -174,6 +174,9 @@ __device__ __forceinline__ void sts_row(T* p, const T (&a)[L]) {
         *reinterpret_cast<double2*>(p + c) = make_double2(a[c], a[c + 1]);
       }
     }
+  } else if constexpr (sizeof(T) == 4 && (L % 2) == 0) {
+#pragma unroll
+    for (int c = 0; c < L; c += 2) *reinterpret_cast<float2*>(p + c) = make_float2(a[c], a[c + 1]);
   } else {
 #pragma unroll
     for (int c = 0; c < L; ++c) p[c] = a[c];

@@ -172,6 +172,13 @@ __device__ __forceinline__ void stg_row(T* p, const T (&a)[L], bool vec_ok) {
       return;
     }
   }
+  if constexpr (sizeof(T) == 4 && (L % 2) == 0) {
+    if (vec_ok) {                       // 8-byte stores: rows start at multiples of ell elements from a 16-byte aligned base
+#pragma unroll
+      for (int c = 0; c < L; c += 2) *reinterpret_cast<float2*>(p + c) = make_float2(a[c], a[c + 1]);
+      return;
+    }
+  }
 #pragma unroll
   for (int c = 0; c < L; ++c) p[c] = a[c];
 }
