@@ -371,7 +371,16 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
     // accumulated in the registers that hold Di^T Di; operands are rows of B and C.  Unrolled: the
     // accumulators need static indices.  Rows then go from registers straight to global memory
     // (gR_{2e} = gd Sigma - gm w w^T at the top level).
+    // At the top level the rows of the two off-diagonal results are turned into gradients in the same pass, right
+    // after their last use (gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T), gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)).
     if (valid) {
+      T we[L], wl[L];
+#pragma unroll
+      for (int c = 0; c < L; ++c) { we[c] = T(0); wl[c] = T(0); }
+      if (grad && do_w) {
+        if (has_odd) lds_row<T, L>(we, N + Cf::WT);
+        if (has_left) lds_row<T, L>(wl, Lf + Cf::WT);
+      }
 #pragma unroll
       for (int k = 0; k < L; ++k) {
         T bk[L];
@@ -380,6 +389,11 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
         for (int r = 0; r < L; ++r)
 #pragma unroll
           for (int c = 0; c <= r; ++c) Mx[r][c] = fma(-bk[r], P[k][c], Mx[r][c]);
+        if (grad && has_odd) {
+#pragma unroll
+          for (int c = 0; c < L; ++c) bk[c] = T(2) * (gd * bk[c] - gm * we[k] * wv[c]);
+          sts_row<T, L>(N + Cf::B + k * L, bk);
+        }
       }
       T* dst = gSd + (size_t)(2 * e) * BS;
 #pragma unroll
@@ -392,6 +406,11 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
 #pragma unroll
           for (int k = 0; k < L; ++k) s = fma(-cr[k], Q[k][c], s);
           Mx[r][c] = s;
+        }
+        if (grad && has_left) {
+#pragma unroll
+          for (int c = 0; c < L; ++c) cr[c] = T(2) * (gd * cr[c] - gm * wv[r] * wl[c]);
+          sts_row<T, L>(N + Cf::C + r * L, cr);
         }
       }
 #pragma unroll
@@ -411,37 +430,18 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   __syncwarp();   // neighbours are done reading this record's S~_d / WT
 
   if (grad) {
-    T we[L], wl[L];
+    T we[L];
 #pragma unroll
-    for (int c = 0; c < L; ++c) { we[c] = T(0); wl[c] = T(0); }
-    if (do_w) {
-      if (has_odd) lds_row<T, L>(we, N + Cf::WT);
-      if (has_left) lds_row<T, L>(wl, Lf + Cf::WT);
-    }
-    if (do_sigma) {
-      if (has_odd) {               // gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T ; gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T)
+    for (int c = 0; c < L; ++c) we[c] = T(0);
+    if (do_w && has_odd) lds_row<T, L>(we, N + Cf::WT);
+    if (do_sigma && has_odd) {     // gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T   (gO rows were finished above)
 #pragma unroll
-        for (int r = 0; r < L; ++r) {
-          T v[L];
-          lds_row<T, L>(v, N + Cf::SD + r * L);
+      for (int r = 0; r < L; ++r) {
+        T v[L];
+        lds_row<T, L>(v, N + Cf::SD + r * L);
 #pragma unroll
-          for (int c = 0; c < L; ++c) v[c] = gd * v[c] - gm * we[r] * we[c];
-          sts_row<T, L>(N + Cf::SD + r * L, v);
-          lds_row<T, L>(v, N + Cf::B + r * L);
-#pragma unroll
-          for (int c = 0; c < L; ++c) v[c] = T(2) * (gd * v[c] - gm * we[r] * wv[c]);
-          sts_row<T, L>(N + Cf::B + r * L, v);
-        }
-      }
-      if (has_left) {              // gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)
-#pragma unroll
-        for (int r = 0; r < L; ++r) {
-          T v[L];
-          lds_row<T, L>(v, N + Cf::C + r * L);
-#pragma unroll
-          for (int c = 0; c < L; ++c) v[c] = T(2) * (gd * v[c] - gm * wv[r] * wl[c]);
-          sts_row<T, L>(N + Cf::C + r * L, v);
-        }
+        for (int c = 0; c < L; ++c) v[c] = gd * v[c] - gm * we[r] * we[c];
+        sts_row<T, L>(N + Cf::SD + r * L, v);
       }
     }
     __syncwarp();   // every lane has read its neighbours' untransformed w~ before anyone rescales it
