@@ -9,7 +9,11 @@ Workload (BASELINE.json configs[1]): B = 1024 independent LEG series x n = 10^4 
 l = 8, fp32, synthetic posterior-precision blocks; every rank holds its own 1024
 series (batch-sharded, weak scaling; the only collective is the all-reduce of the summed
 log-likelihood scalar).  A "step" = one forward + backward pass over the rank's batch.
-One JSON line is printed by rank 0."""
+One JSON line is printed by rank 0.  Besides the headline (`value`, weak scaling) the line carries
+  strong       the same workload with 1024 series in TOTAL (1024 / N per GPU),
+  long_series  BASELINE configs[3]: ONE series of n = 1e8 rows, l = 4, fp32, chunk-partitioned over the N ranks with one
+               NCCL all-gather (cyclic_gps.distributed), with its own clocks record and a parity block (chunked on N
+               ranks vs the unchunked single sweep at n = 4e6, and the residual of J w = x at the full size)."""
 import argparse
 import json
 import os
@@ -81,14 +85,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self, busy=None):
-        """`busy`: callable that keeps the GPU under the benchmark's load; nvidia-smi needs a few hundred ms to
-        deliver its first line, so short runs repeat the workload until at least two samples exist (<= 3 s)."""
+    def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        t0 = time.perf_counter()
-        while busy is not None and len(self.lines) < 2 and time.perf_counter() - t0 < 3.0:
-            busy()
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -110,6 +109,24 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def keep_busy_until_sampled(sampler, step, rank, world, dist, dev, min_samples=5, max_s=8.0):
+    """nvidia-smi needs a few hundred ms per line; short timed regions are followed by the same steps, run by ALL
+    ranks together (rank 0 decides when to stop and broadcasts it), until rank 0 holds `min_samples` lines taken
+    under the benchmark's own load."""
+    t0 = time.perf_counter()
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    while True:
+        step()
+        torch.cuda.synchronize()
+        done = sampler is None or sampler.proc is None or len(sampler.lines) >= min_samples or time.perf_counter() - t0 > max_s
+        if world > 1:
+            flag.fill_(1 if done else 0)
+            dist.broadcast(flag, 0)
+            done = bool(int(flag.item()))
+        if done:
+            return
 
 
 class LaunchTrace:
@@ -181,6 +198,15 @@ def workload_name(B, n, ell, dtype_name):
     return f"configs[1]: batched LEG loglik+grad, {B} series x n={n}, l={ell}, {dtype_name}, batch-sharded"
 
 
+def batch_config(B, n, ell, dtype_name, world):
+    """`config` of the JSON line; the reference arm prints the very same dict (the driver compares them)."""
+    s = 4 if dtype_name == "float32" else 8
+    in_bytes = (B * n * ell * ell + B * (n - 1) * ell * ell + B * n * ell) * s
+    return {"workload": workload_name(B, n, ell, dtype_name), "batch_per_gpu": B, "n": n, "ell": ell,
+            "parallelism": f"batch-shard x{world}",
+            "l2": "inputs per step (%.1f GB) exceed L2 (126 MB); no explicit flush" % (in_bytes / 1e9)}
+
+
 def run_reference(args):
     """--impl reference: the reference CPU implementation of the path (oracle port of
     cyclic_reduction.py + torch autograd, all host threads), bounded sample per step."""
@@ -201,40 +227,145 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(WORKLOAD["batch"], n, ell, WORKLOAD["dtype"]),
-                       "batch_per_gpu": WORKLOAD["batch"], "n": n, "ell": ell,
-                       "reference_sample": f"{series_per_step} of {WORKLOAD['batch']} series per step, reference CPU path (oracle port), "
-                                           "one series at a time"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": batch_config(WORKLOAD["batch"], n, ell, WORKLOAD["dtype"], args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample + "; reference CPU path = oracle port of cyclic_reduction.py + torch autograd"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def run_long(args):
+class Ranks:
+    """Process-group plumbing shared by the workloads of one bench.py run."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def sync(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def long_rows(lo, hi, n, ell, dtype, dev, seed):
+    """Rows [lo, hi) of THE global long series (gaps and right-hand side are functions of the global row index
+    only, so any partition over ranks sees the same series)."""
+    from cyclic_gps.synth import gaps_for_rows, leg_params, leg_precision_rows, x_for_rows
+    G, Bm, LLT = leg_params(ell, seed=0, device=dev)
+    R, Oprev = leg_precision_rows(gaps_for_rows(lo, hi, n, seed=seed, device=dev), G, Bm, LLT, dtype)
+    return R, Oprev, x_for_rows(lo, hi, ell, seed + 1, dev, dtype)
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300)) if b.numel() else 0.0
+
+
+def long_parity(rk, ell, dtype, n_par, sub):
+    """Chunk-partitioned path on `world` ranks (NCCL all-gather when world > 1) against the plain single-sweep path
+    of the same library on rank 0, same global series: mahal, logdet and the gradients of the rows rank 0 owns."""
+    from cyclic_gps import cyclic_reduction as cr, distributed as D
+    plan = D.make_plan(n_par, rk.world, sub=sub)
+    lo, hi = plan.rows(rk.rank)
+    R, Oprev, x = long_rows(lo, hi, n_par, ell, dtype, rk.dev, seed=11)
+    R.requires_grad_(True); Oprev.requires_grad_(True); x.requires_grad_(True)
+    mh, ld = D.chunked_mahal_and_det(R, Oprev, x, plan, rk.rank)
+    (mh + ld).backward()
+    out = None
+    if rk.rank == 0:
+        Rf, Of, xf = long_rows(0, n_par, n_par, ell, dtype, rk.dev, seed=11)
+        Rf.requires_grad_(True); xf.requires_grad_(True)
+        Os = Of[1:].clone().requires_grad_(True)
+        m1, d1 = cr.mahal_and_det(Rf, Os, xf)
+        (m1 + d1).backward()
+        gOprev = torch.cat([torch.zeros_like(Os.grad[:1]), Os.grad], dim=0)
+        out = {"n": n_par, "ranks": rk.world, "backend": "nccl" if rk.world > 1 else "single process",
+               "sub_chunk_rows": plan.sub, "rows_checked_for_gradients": hi - lo,
+               "mahal_rel": _rel(mh, m1), "logdet_rel": _rel(ld, d1),
+               "gR_rel": _rel(R.grad, Rf.grad[lo:hi]), "gO_rel": _rel(Oprev.grad, gOprev[lo:hi]), "gx_rel": _rel(x.grad, xf.grad[lo:hi]),
+               "tolerance": 1e-4}
+        out["ok"] = all(out[k] <= out["tolerance"] for k in ("mahal_rel", "logdet_rel", "gR_rel", "gO_rel", "gx_rel"))
+    rk.sync()
+    return out
+
+
+def long_residual(rk, R, Oprev, x, w, chunk=1 << 22):
+    """max |J w - x| / max |x| over ALL rows of the distributed series: every rank needs w of the row before its first
+    and after its last row, and the coupling block of the row after its last (one tiny all-gather)."""
+    ell = R.shape[-1]
+    n_loc = R.shape[0]
+    z = lambda *sh: torch.zeros(sh, dtype=torch.float64, device=rk.dev)
+    mine = torch.cat([(w[:1].double().reshape(-1) if n_loc else z(ell)), (w[-1:].double().reshape(-1) if n_loc else z(ell)),
+                      (Oprev[:1].double().reshape(-1) if n_loc else z(ell * ell)), torch.tensor([float(n_loc > 0)], dtype=torch.float64, device=rk.dev)])
+    if rk.dist is not None:
+        allv = torch.empty((rk.world, mine.numel()), dtype=torch.float64, device=rk.dev)
+        rk.dist.all_gather_into_tensor(allv, mine.unsqueeze(0))
+    else:
+        allv = mine.unsqueeze(0)
+    prev = [r for r in range(rk.rank) if allv[r, -1] > 0]
+    nxt = [r for r in range(rk.rank + 1, rk.world) if allv[r, -1] > 0]
+    w_before = allv[prev[-1], ell:2 * ell] if prev else z(ell)
+    w_after = allv[nxt[0], 0:ell] if nxt else z(ell)
+    O_after = allv[nxt[0], 2 * ell:2 * ell + ell * ell].view(ell, ell) if nxt else z(ell, ell)
+    worst = z(1)
+    xmax = x.detach().abs().max().double().reshape(1) if n_loc else z(1)
+    for a in range(0, n_loc, chunk):
+        b = min(a + chunk, n_loc)
+        wd = w[a:b].double()
+        r = torch.einsum("nij,nj->ni", R[a:b].detach().double(), wd) - x[a:b].detach().double()
+        wl = torch.cat([(w[a - 1:a].double() if a > 0 else w_before.view(1, ell)), wd[:-1]], dim=0)
+        r += torch.einsum("nij,nj->ni", Oprev[a:b].detach().double(), wl)
+        On = torch.cat([Oprev[a + 1:b].detach().double(), (Oprev[b:b + 1].detach().double() if b < n_loc else O_after.view(1, ell, ell))], dim=0)
+        wr = torch.cat([wd[1:], (w[b:b + 1].double() if b < n_loc else w_after.view(1, ell))], dim=0)
+        r += torch.einsum("nji,nj->ni", On, wr)
+        worst = torch.maximum(worst, r.abs().max().reshape(1))
+    if rk.dist is not None:
+        rk.dist.all_reduce(worst, op=rk.dist.ReduceOp.MAX)
+        rk.dist.all_reduce(xmax, op=rk.dist.ReduceOp.MAX)
+    return float(worst / xmax)
+
+
+def run_long(args, rk, standalone):
     """BASELINE configs[3]: ONE series of n rows (default 1e8), l = 4, fp32, rows spread over the ranks
-    (chunk-partitioned CR, cyclic_gps.distributed); strong scaling.  step = loglik forward + backward."""
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    (chunk-partitioned CR + one NCCL all-gather, cyclic_gps.distributed); strong scaling.  step = loglik forward +
+    backward.  Returns the result dict on rank 0 (None elsewhere)."""
     from cyclic_gps import _native, distributed as D
-    from cyclic_gps.synth import gaps_for_rows, leg_params, leg_precision_rows
-    _native.load()
-    n, ell = args.n, args.ell
-    dtype = getattr(torch, args.dtype)
+    rank, world, dev, dist = rk.rank, rk.world, rk.dev, rk.dist
+    n, ell = args.long_n, args.long_ell
+    dtype = getattr(torch, args.long_dtype)
     s = torch.empty((), dtype=dtype).element_size()
+    D.DEFERRED_PD_CHECK = True                 # this loop always runs backward(): no GPU drain between the passes
+    D.RELEASE_FACTORS_AFTER_BACKWARD = True
+    parity = None
+    if not args.no_parity:
+        parity = long_parity(rk, ell, dtype, min(args.parity_n, n), None)
+        torch.cuda.empty_cache()
     plan = D.make_plan(n, world, sub=args.sub)
     lo, hi = plan.rows(rank)
-    G, Bm, LLT = leg_params(ell, seed=0, device=dev)
-    R, Oprev = leg_precision_rows(gaps_for_rows(lo, hi, n, seed=7, device=dev), G, Bm, LLT, dtype)
-    gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    x = torch.randn((hi - lo, ell), generator=gen, dtype=dtype, device=dev)
+    R, Oprev, x = long_rows(lo, hi, n, ell, dtype, dev, seed=7)
     R.requires_grad_(True); Oprev.requires_grad_(True); x.requires_grad_(True)
 
     def step():
@@ -244,19 +375,13 @@ def run_long(args):
         ll.backward()
         return ll
 
-    def sync():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3) + 2):          # two extra: the caching allocator needs them to settle at this size
         step()
     trace = LaunchTrace()
     _native.TRACE = trace
-    clocks = ClockSampler(local)
-    sync()
-    if rank == 0:
+    clocks = ClockSampler(rk.local) if rank == 0 else None
+    rk.sync()
+    if clocks is not None:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lc0 = _native.launch_count()
@@ -264,60 +389,51 @@ def run_long(args):
     for _ in range(args.steps):
         ll = step().detach()
     e1.record()
-    sync()
+    rk.sync()
     ms = e0.elapsed_time(e1)
     timed_launches = _native.launch_count() - lc0       # kernels of libcrb200 launched inside the timed region
     trace.enabled = True
     for _ in range(min(args.steps, 2)):
         step()
-    sync()
+    rk.sync()
     trace.enabled = False
-    def _busy():
-        step()
-        torch.cuda.synchronize()
-    clk = clocks.stop(busy=_busy if world == 1 else None) if rank == 0 else None   # (extra steps on one rank only would hang a collective)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+    keep_busy_until_sampled(clocks, step, rank, world, dist, dev)       # all ranks keep stepping until rank 0 has its samples
+    clk = clocks.stop() if clocks is not None else None
+    _native.TRACE = None
+    ms = rk.max_over_ranks(ms)
+    # J w = x at the full size: x.grad of the last step is d(-0.5 mahal)/dx = -w
+    residual = None
+    if not args.no_parity:
+        residual = long_residual(rk, R, Oprev, x, -x.grad)
     if rank != 0:
-        dist.destroy_process_group()
-        return
+        return None
     peak, peak_src = peaks()
     agg = trace.summary()
     table = []
     for (kind, m, batch), (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         avg_ms = tot / cnt
         algo = bytes_per_row_level(ell, s) * m * batch
-        table.append({"kernel": f"cr_{kernel_family(ell, s)}_{kind}_kernel<{args.dtype},{ell}>", "m": m, "batch": batch, "launches": cnt, "avg_ms": avg_ms,
+        table.append({"kernel": f"cr_{kernel_family(ell, s)}_{kind}_kernel<{args.long_dtype},{ell}>", "m": m, "batch": batch, "launches": cnt, "avg_ms": avg_ms,
                       "algo_bytes": algo, "achieved_gbs": algo / (avg_ms * 1e-3) / 1e9, "frac": algo / (avg_ms * 1e-3) / 1e9 / peak})
     top = table[0]
     whole = bytes_per_row_total(ell, s) * (hi - lo)
     roofline = {"bound": "hbm", "kernel": top["kernel"] + f" @ m={top['m']} x batch {top['batch']}", "achieved": top["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": top["frac"], "traffic": None, "peak_source": peak_src,
-                "whole_step_rank0": {"algo_bytes": whole, "achieved": whole / (ms / args.steps * 1e-3) / 1e9,
+                "whole_step_rank0": {"rows": hi - lo, "algo_bytes": whole, "achieved": whole / (ms / args.steps * 1e-3) / 1e9,
                                      "frac": whole / (ms / args.steps * 1e-3) / 1e9 / peak}}
-    if args.levels_out:
+    if args.levels_out and standalone:
         os.makedirs(os.path.dirname(os.path.abspath(args.levels_out)), exist_ok=True)
         with open(args.levels_out, "w") as fh:
             json.dump(table, fh, indent=1)
-    cpu = None
-    if not args.no_cpu_baseline:
-        ncpu = min(n, 1_000_000)
-        v, dt = cpu_reference_rows_per_s(ncpu, ell, dtype, 3, warm=1)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"3 passes over a series of n={ncpu} (of {n}; host RAM bounds the reference at ~628 B/row), l={ell}, {args.dtype}, {dt:.1f} s"}
-    line = {"metric": METRIC, "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-            "config": {"workload": f"configs[3]: single long series n={n}, l={ell}, {args.dtype}, chunk-partitioned CR + one all-gather",
-                       "n": n, "ell": ell, "sub_chunk_rows": plan.sub, "sub_chunks": plan.nsub, "parallelism": f"row-chunks x{world}",
-                       "l2": "inputs per step exceed L2; no explicit flush"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "gpu_launches": timed_launches,
-            "clocks": clk, "loglik": float(ll)}
-    emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    if parity is not None:
+        parity["residual_Jw_minus_x_rel_full_n"] = residual
+        parity["ok"] = bool(parity["ok"] and residual is not None and residual <= 1e-4)
+    return {"workload": f"configs[3]: single long series n={n}, l={ell}, {args.long_dtype}, chunk-partitioned CR + one all-gather",
+            "metric": METRIC, "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "ms_per_step": ms / args.steps, "scaling": "strong", "n": n, "ell": ell, "dtype": "f32" if dtype == torch.float32 else "f64",
+            "sub_chunk_rows": plan.sub, "sub_chunks": plan.nsub, "parallelism": f"row-chunks x{world}",
+            "collective": "one all_gather_into_tensor (nccl) of the boundary system per forward pass" if world > 1 else "none (one rank)",
+            "roofline": roofline, "gpu_launches": timed_launches, "clocks": clk, "parity": parity, "loglik": float(ll)}
 
 
 _REAL_STDOUT = None
@@ -343,6 +459,37 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def time_batch(rk, cr, tensors, steps, warmup):
+    """K timed loglik+grad steps over this rank's series; returns (ms max over ranks, step fn, checksum, launches)."""
+    from cyclic_gps import _native
+    Rr, Or, xr = tensors
+    dist = rk.dist
+    total = torch.zeros((), dtype=torch.float64, device=rk.dev)
+
+    def step():
+        Rr.grad = Or.grad = xr.grad = None
+        mm, dd = cr.mahal_and_det(Rr, Or, xr)
+        ll = -0.5 * (mm.double().sum() + dd.double().sum())
+        ll.backward()
+        tot = ll.detach().clone()
+        if dist is not None:
+            dist.all_reduce(tot)          # the job-wide log-likelihood (the only collective of this workload)
+        return tot
+
+    for _ in range(warmup):
+        step()
+    rk.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lc0 = _native.launch_count()
+    e0.record()
+    for _ in range(steps):
+        total += step().detach()
+    e1.record()
+    rk.sync()
+    ms = rk.max_over_ranks(e0.elapsed_time(e1))
+    return ms, step, float(total) / max(steps, 1), _native.launch_count() - lc0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,97 +502,96 @@ def main():
     ap.add_argument("--dtype", default=WORKLOAD["dtype"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-long", action="store_true", help="skip the long_series object (configs[3])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling run of configs[1]")
+    ap.add_argument("--no-parity", action="store_true", help="long series: skip the parity block")
     ap.add_argument("--levels-out", default=None, help="write the per-level launch table (JSON) here")
     ap.add_argument("--workload", default="batch", choices=["batch", "long"],
-                    help="batch = configs[1] (default, the headline metric); long = configs[3], one series of --n rows")
+                    help="batch = configs[1] headline + strong + long_series (default); long = only configs[3], printed as the line")
+    ap.add_argument("--long-n", type=int, default=100_000_000)
+    ap.add_argument("--long-ell", type=int, default=4)
+    ap.add_argument("--long-dtype", default="float32")
+    ap.add_argument("--parity-n", type=int, default=4_000_000)
     ap.add_argument("--sub", type=int, default=None, help="long workload: rows per sub-chunk (power of two)")
     ap.add_argument("--variant", type=int, default=0, help="force a kernel family (0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "long":
-        if args.n == WORKLOAD["n"]:
-            args.n, args.ell = 100_000_000, 4
-        return run_long(args)
     args.warmup = max(args.warmup, 3)
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rk = Ranks()
+    rank, world, dev, dist = rk.rank, rk.world, rk.dev, rk.dist
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
     from cyclic_gps import _native, cyclic_reduction as cr
     _native.load()
     _native.VARIANT = args.variant
+
+    if args.workload == "long":
+        res = run_long(args, rk, standalone=True)
+        if rank == 0:
+            cpu = None
+            if not args.no_cpu_baseline:
+                ncpu = min(args.long_n, 1_000_000)
+                dt_ = getattr(torch, args.long_dtype)
+                v, dt = cpu_reference_rows_per_s(ncpu, args.long_ell, dt_, 3, warm=1)
+                cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": f"3 passes over a series of n={ncpu} (of {args.long_n}; host RAM bounds the reference at ~628 B/row), "
+                                 f"l={args.long_ell}, {args.long_dtype}, {dt:.1f} s"}
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": res["dtype"], "data": "synthetic",
+                    "config": {"workload": res["workload"], "n": res["n"], "ell": res["ell"], "sub_chunk_rows": res["sub_chunk_rows"],
+                               "sub_chunks": res["sub_chunks"], "parallelism": res["parallelism"],
+                               "l2": "inputs per step exceed L2; no explicit flush"},
+                    "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": None, "gpu_launches": res["gpu_launches"],
+                    "clocks": res["clocks"], "parity": res["parity"], "loglik": res["loglik"]}
+            emit(line)
+        rk.close()
+        return
+
+    # the timed loops always run backward(): opt into the deferred non-PD report and the early release of the factors
+    cr.EAGER_PD_CHECK = False
+    cr.RELEASE_FACTORS_AFTER_BACKWARD = True
     B, n, ell = args.batch, args.n, args.ell
     dtype = getattr(torch, args.dtype)
     s = torch.empty((), dtype=dtype).element_size()
     R, O, x = make_inputs(dev, 1000 + rank, B, n, ell, dtype)
     Rr, Or, xr = R.requires_grad_(True), O.requires_grad_(True), x.requires_grad_(True)
-    total = torch.zeros((), dtype=torch.float64, device=dev)
 
-    def step():
-        Rr.grad = Or.grad = xr.grad = None
-        mm, dd = cr.mahal_and_det(Rr, Or, xr)
-        ll = -0.5 * (mm.double().sum() + dd.double().sum())
-        ll.backward()
-        tot = ll.detach().clone()
-        if dist is not None:
-            dist.all_reduce(tot)          # the job-wide log-likelihood (the only collective of this workload)
-        return tot
-
-    def sync():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
+    # ---- pass 1: the headline timing (weak scaling: B series on every rank; no per-launch events inside)
+    clocks = ClockSampler(rk.local) if rank == 0 else None
+    if clocks is not None:
+        clocks.start()
+    ms, step, checksum, timed_launches = time_batch(rk, cr, (Rr, Or, xr), args.steps, args.warmup)
+    # ---- pass 2: same steps with an event pair around every launch (per-kernel durations, roofline)
     trace = LaunchTrace()
     _native.TRACE = trace
-    clocks = ClockSampler(local)
-    sync()
-    if rank == 0:
-        clocks.start()
-    # pass 1: the headline timing (no per-launch events inside)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lc0 = _native.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        total += step().detach()
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
-    timed_launches = _native.launch_count() - lc0       # kernels of libcrb200 launched inside the timed region
-    # pass 2: same steps with an event pair around every launch (per-kernel durations, roofline)
     trace.enabled = True
     for _ in range(args.steps):
         step()
-    sync()
+    rk.sync()
     trace.enabled = False
-    def _busy():
-        step()
-        torch.cuda.synchronize()
-    clk = clocks.stop(busy=_busy if world == 1 else None) if rank == 0 else None   # (extra steps on one rank only would hang a collective)
+    _native.TRACE = None
+    keep_busy_until_sampled(clocks, step, rank, world, dist, dev)
+    clk = clocks.stop() if clocks is not None else None
     launches_per_step = len(trace.records) // max(args.steps, 1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
     rows = B * n * world
     value = rows * args.steps / (ms * 1e-3)
+
+    # ---- strong scaling of the same workload: B series in TOTAL, B / world per rank
+    strong = None
+    if not args.no_strong:
+        if world == 1:
+            strong = {"series_total": B, "series_per_gpu": B, "ms_per_step": ms / args.steps, "value": value, "unit": UNIT,
+                      "note": "one GPU: identical to the headline run"}
+        elif B % world == 0:
+            Bs = B // world
+            sub_t = tuple(t.detach()[:Bs].requires_grad_(True) for t in (R, O, x))
+            ms_s, _, _, _ = time_batch(rk, cr, sub_t, args.steps, args.warmup)
+            strong = {"series_total": B, "series_per_gpu": Bs, "ms_per_step": ms_s / args.steps,
+                      "value": B * n * args.steps / (ms_s * 1e-3), "unit": UNIT}
+            del sub_t
 
     # ---- end to end: host buffers in, scalars out, copies inside the timed region
     e2e = None
@@ -463,8 +609,8 @@ def main():
         def e2e_step():
             """Host buffers in, per-series scalars out, through the public API (cr.mahal_and_det + backward).
             The batch is cut into chunks of series; chunk c+1 crosses PCIe on a copy stream while chunk c computes."""
-            main = torch.cuda.current_stream()
-            copy_stream.wait_stream(main)                 # previous step is done with the device buffers
+            main_s = torch.cuda.current_stream()
+            copy_stream.wait_stream(main_s)               # previous step is done with the device buffers
             ready = []
             with torch.cuda.stream(copy_stream):
                 for c in range(nchunk):
@@ -478,7 +624,7 @@ def main():
             tot = torch.zeros((), dtype=torch.float64, device=dev)
             for c in range(nchunk):
                 sl = slice(c * bsz, (c + 1) * bsz)
-                main.wait_event(ready[c])
+                main_s.wait_event(ready[c])
                 Rc, Oc, xc = (t[sl].detach().requires_grad_(True) for t in (dR, dO, dx))
                 mm, dd = cr.mahal_and_det(Rc, Oc, xc)
                 ll = -0.5 * (mm.double().sum() + dd.double().sum())
@@ -488,33 +634,35 @@ def main():
                 hout[1, sl].copy_(dd.detach(), non_blocking=True)
             if dist is not None:
                 dist.all_reduce(tot)
-            main.synchronize()                            # the caller holds the result on the host
+            main_s.synchronize()                          # the caller holds the result on the host
             return hout
 
         e2e_step()
-        sync()
+        rk.sync()
         k2 = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(k2):
             e2e_step()
         a1.record()
-        sync()
-        ms2 = a0.elapsed_time(a1) / k2
-        if dist is not None:
-            t = torch.tensor([ms2], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t)
+        rk.sync()
+        ms2 = rk.max_over_ranks(a0.elapsed_time(a1) / k2)
         h2d = (hR.numel() + hO.numel() + hx.numel()) * s
         e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
                "ms_per_step": ms2, "steps": k2, "pipeline": f"{nchunk} chunks of {bsz} series, H2D on a copy stream overlapped with compute",
                "h2d_gbs": h2d / (ms2 * 1e-3) / 1e9}
         del hR, hO, hx, dR, dO, dx
 
+    # ---- configs[3]: the single long series over the same ranks
+    del R, O, x, Rr, Or, xr, step
+    torch.cuda.empty_cache()
+    long_series = None
+    if not args.no_long:
+        long_series = run_long(args, rk, standalone=False)
+        torch.cuda.empty_cache()
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        rk.close()
         return
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event durations)
@@ -565,15 +713,12 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(B, n, ell, args.dtype),
-                       "batch_per_gpu": B, "n": n, "ell": ell, "parallelism": f"batch-shard x{world}",
-                       "l2": "inputs per step (%.1f GB) exceed L2 (126 MB); no explicit flush" % ((R.numel() + O.numel() + x.numel()) * s / 1e9)},
+            "config": batch_config(B, n, ell, args.dtype, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches,
             "gpu_launches_per_step": timed_launches // max(args.steps, 1), "per_level_table_launches_per_step": launches_per_step, "clocks": clk,
-            "loglik_checksum": float(total) / max(args.steps, 1)}
+            "loglik_checksum": checksum, "strong": strong, "long_series": long_series}
     emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    rk.close()
 
 
 if __name__ == "__main__":

@@ -59,15 +59,22 @@ cudaError_t bwd_multi(int dtype, int ell, const crb200::MultiArgs<crb200_bwd_arg
 // its CTA resident at once (two CTAs per SM at the largest record): small batches -- single series, sub-chunk batches
 // of the chunked path, boundary systems.  Measured on configs[1] (1024 series): 9.9 ms fused vs 9.3 ms per-level.
 bool batch_fits_one_wave(int batch) {
-  static int sms[64] = {0};
+  static std::atomic<int> sms[64];                            // SM count per device, 0 = not asked yet (a race only repeats the query)
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-  if (sms[dev] == 0) {
-    int v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return false;
+  int v = dev < 64 ? sms[dev].load(std::memory_order_relaxed) : 0;
+  if (v == 0) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return false;
-    sms[dev] = v;
+    if (dev < 64) sms[dev].store(v, std::memory_order_relaxed);
   }
-  return batch <= 2 * sms[dev];
+  return batch <= 2 * v;
+}
+
+// number of CR levels of an n-row system: floor(log2 n) + 1
+int max_levels(int n) {
+  int L = 0;
+  for (int m = n; m >= 1; m /= 2) ++L;
+  return L;
 }
 
 // First level of the fused tail of a sweep over levels 0..L-1 of an n-row system, or L when nothing is fused.
@@ -148,6 +155,7 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
   if (a == nullptr) return CRB200_EINVAL;
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
   if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->R == nullptr) return CRB200_EINVAL;
+  if (a->nlevels > max_levels(a->n)) return CRB200_EINVAL;   // checked before anything is launched
   const int es = dtype == CRB200_F32 ? 4 : 8;
   const long long bs = (long long)ell * ell, B = a->batch;
   crb200_fwd_args l{};
@@ -229,6 +237,7 @@ int crb200_sweep_halfsolve(int dtype, int ell, const crb200_sweep_hs_args* a, vo
   if (a == nullptr) return CRB200_EINVAL;
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
   if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->D == nullptr || a->y == nullptr || a->X == nullptr) return CRB200_EINVAL;
+  if (a->nlevels > max_levels(a->n)) return CRB200_EINVAL;
   const int es = dtype == CRB200_F32 ? 4 : 8;
   const long long bs = (long long)ell * ell, B = a->batch;
   crb200_hs_args l{};
@@ -258,6 +267,7 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
   if (a == nullptr) return CRB200_EINVAL;
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
   if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->nlevels > 40 || a->D == nullptr) return CRB200_EINVAL;
+  if (a->nlevels > max_levels(a->n)) return CRB200_EINVAL;
   const int es = dtype == CRB200_F32 ? 4 : 8;
   const long long bs = (long long)ell * ell, B = a->batch;
   int ms[40];

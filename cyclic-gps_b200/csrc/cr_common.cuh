@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "crb200.h"
 
 namespace crb200 {
@@ -18,6 +19,24 @@ template <int L>
 struct GroupLanes {
   static constexpr int value = L <= 1 ? 1 : L <= 2 ? 2 : L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32;
 };
+
+constexpr int kMaxDevices = 64;
+
+// Opt a kernel into its dynamic shared-memory size once per device.  Thread-safe (the flags are atomics; a race only
+// repeats the idempotent attribute call); devices beyond kMaxDevices set the attribute on every launch.  The CURRENT
+// device must be the one that owns the stream the kernel is launched on (include/crb200.h, "Threading").
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned char>* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (tracked) done[dev].store(1, std::memory_order_release);
+  return cudaSuccess;
+}
 
 __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }

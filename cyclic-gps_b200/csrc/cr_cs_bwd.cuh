@@ -367,14 +367,8 @@ cr_cs_bwd_kernel(const LevelBwdArgs a) {
 template <typename T, int L, int LPN>
 cudaError_t launch_cs_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   using C = CsBwdCfg<T, L, LPN>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_cs_bwd_kernel<T, L, LPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_cs_bwd_kernel<T, L, LPN>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::NT - 1) / C::NT;
   const long long grid = tiles * a.batch;

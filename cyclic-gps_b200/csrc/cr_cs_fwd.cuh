@@ -319,14 +319,8 @@ cr_cs_fwd_kernel(const LevelFwdArgs a) {
 template <typename T, int L, int LPN>
 cudaError_t launch_cs_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   using C = CsFwdCfg<T, L, LPN>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_cs_fwd_kernel<T, L, LPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_cs_fwd_kernel<T, L, LPN>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::OWN - 1) / C::OWN;
   const long long grid = tiles * a.batch;

@@ -305,14 +305,8 @@ cr_level_fwd_kernel(const LevelFwdArgs a) {
 template <typename T, int L>
 cudaError_t launch_level_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   using C = FwdCfg<T, L>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_level_fwd_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_level_fwd_kernel<T, L>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + (C::NG - 1) - 1) / (C::NG - 1);
   const long long grid = tiles * a.batch;

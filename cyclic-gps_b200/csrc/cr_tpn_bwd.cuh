@@ -1,4 +1,4 @@
-// Thread-per-node backward level kernel for small blocks (sizeof(T) * ell^2 <= 256 bytes).
+// Thread-per-node backward level kernel for small blocks (sizeof(T) * ell^2 <= CRB200_TPN_MAX_BLOCK_BYTES = 400 bytes).
 //
 // Same contract as cr_level_bwd_kernel (cr_level_bwd.cuh: back-half-solve + selected inverse +
 // optional gradient assembly; reference cyclic_gps/cyclic_reduction.py:362-373, :478-501),
@@ -497,14 +497,8 @@ cr_tpn_bwd_multi_kernel(const __grid_constant__ MultiArgs<LevelBwdArgs> ma) {
 template <typename T, int L>
 cudaError_t launch_tpn_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   using C = TpnBwdCfg<T, L>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_tpn_bwd_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_bwd_kernel<T, L>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::NT - 1) / C::NT;
   const long long total = tiles * a.batch;
@@ -519,14 +513,8 @@ template <typename T, int L>
 cudaError_t launch_tpn_bwd_multi(const MultiArgs<LevelBwdArgs>& ma, cudaStream_t stream) {
   using C = TpnBwdCfg<T, L>;
   constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_tpn_bwd_multi_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_bwd_multi_kernel<T, L>, SMEM, attr_done); e != cudaSuccess) return e;
   if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
   cr_tpn_bwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
   return cudaGetLastError();

@@ -1,4 +1,4 @@
-// Thread-per-node forward level kernel for small blocks (sizeof(T) * ell^2 <= 256 bytes).
+// Thread-per-node forward level kernel for small blocks (sizeof(T) * ell^2 <= CRB200_TPN_MAX_BLOCK_BYTES = 400 bytes).
 //
 // Same contract as cr_level_fwd_kernel (see cr_level_fwd.cuh for the maths and the reference
 // lines it replaces: cyclic_gps/cyclic_reduction.py:204-259, :412-427), different mapping:
@@ -65,7 +65,7 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   // ---------------- stage in: two cp.async groups ----------------
   // group 0 = R tile + y (needed first: Cholesky, half solve); group 1 = O tile.  The Cholesky of this CTA
   // overlaps the arrival of group 1, and the factor blocks leave for global memory as soon as they exist,
-  // so one CTA keeps the memory pipe busy through most of its life (only 5 such CTAs fit on an SM).
+  // so one CTA keeps the memory pipe busy through most of its life (8 such CTAs fit on an SM at ell = 8 fp32).
   {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
@@ -425,14 +425,8 @@ cr_tpn_fwd_multi_kernel(const __grid_constant__ MultiArgs<LevelFwdArgs> ma) {
 template <typename T, int L>
 cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   using C = TpnFwdCfg<T, L>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_tpn_fwd_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_fwd_kernel<T, L>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
   const int E = (a.m + 1) / 2;
   const long long tiles = (E + C::OWN - 1) / C::OWN;
   const long long total = tiles * a.batch;
@@ -447,14 +441,8 @@ template <typename T, int L>
 cudaError_t launch_tpn_fwd_multi(const MultiArgs<LevelFwdArgs>& ma, cudaStream_t stream) {
   using C = TpnFwdCfg<T, L>;
   constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(cr_tpn_fwd_multi_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return e;
-    attr_done[dev] = true;
-  }
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_fwd_multi_kernel<T, L>, SMEM, attr_done); e != cudaSuccess) return e;
   if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
   cr_tpn_fwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
   return cudaGetLastError();

@@ -367,12 +367,16 @@ def det(decomp):
     return 2 * total
 
 
-# Under autograd the positive-definiteness report of the forward sweep is fetched asynchronously and raised by the
-# backward pass (after it has queued its kernels): a blocking device->host read at the end of the forward pass drains
-# the GPU and leaves it idle while the host walks from forward to backward (0.1-0.6 ms per step on configs[1],
-# depending on the host).  Forward-only calls always check at once.  Set EAGER_PD_CHECK = True to get the
-# reference's behaviour (NotPSDError raised inside mahal_and_det, cyclic_reduction.py:429) under autograd too.
-EAGER_PD_CHECK = False
+# Error contract (reference cyclic_reduction.py:429: NotPSDError is raised inside mahal_and_det): by default the
+# positive-definiteness report of the forward sweep is read before mahal_and_det returns, with or without autograd.
+# A training loop that is guaranteed to call backward() can opt into the deferred mode (EAGER_PD_CHECK = False): the
+# report is then fetched asynchronously and raised by the backward pass after it has queued its kernels, which
+# avoids draining the GPU between forward and backward (0.1-0.6 ms per step on configs[1]; bench.py opts in).
+EAGER_PD_CHECK = True
+# Memory: the packed factors (~3 n l^2 elements) live as long as the autograd graph, like the reference's tape, so
+# backward(retain_graph=True) and repeated torch.autograd.grad calls work.  RELEASE_FACTORS_AFTER_BACKWARD = True
+# frees them at the end of the first backward pass instead (a second backward then raises); bench.py opts in.
+RELEASE_FACTORS_AFTER_BACKWARD = False
 
 
 class _MahalAndDetFn(torch.autograd.Function):
@@ -404,11 +408,12 @@ class _MahalAndDetFn(torch.autograd.Function):
     def backward(ctx, g_mahal, g_det):
         pack = ctx.pack
         if pack is None:
-            raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
+            raise RuntimeError("the CR factors were released by the first backward pass (RELEASE_FACTORS_AFTER_BACKWARD is set)")
         dev = pack.device
         as_vec = lambda g: g.detach().to(dev, torch.float64).reshape(-1).expand(pack.batch).contiguous()
         gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(as_vec(g_mahal), as_vec(g_det)))
-        ctx.pack = None                                # free the packed factors (~3 n l^2 elements) right away
+        if RELEASE_FACTORS_AFTER_BACKWARD:
+            ctx.pack = None                            # free the packed factors (~3 n l^2 elements) right away
         if ctx.deferred is not None:
             deferred, ctx.deferred = ctx.deferred, None
             deferred.wait()                            # NotPositiveDefiniteError of the forward sweep surfaces here

@@ -49,7 +49,7 @@ class ChunkPlan:
 
     def rows(self, rank: int) -> Tuple[int, int]:
         a, b = self.bounds[rank]
-        return a * self.sub, min(b * self.sub, self.n)
+        return min(a * self.sub, self.n), min(b * self.sub, self.n)   # ranks beyond the last sub-chunk own nothing
 
     def full_subchunks(self, rank: int) -> int:
         lo, hi = self.rows(rank)
@@ -72,7 +72,9 @@ def make_plan(n: int, world: int, sub: Optional[int] = None, per_rank: int = 12)
         sub = min(sub, 1 << 22)
     if sub < 2 or sub & (sub - 1):
         raise ValueError("sub must be a power of two >= 2")
-    nsub = (n + sub - 1) // sub
+    if n < 1 or world < 1:
+        raise ValueError("need n >= 1 rows and world >= 1 ranks")
+    nsub = (n + sub - 1) // sub          # may be < world: the surplus ranks get an empty row range
     base, extra = divmod(nsub, world)
     bounds, pos = [], 0
     for r in range(world):
@@ -95,6 +97,12 @@ def _gather(t: torch.Tensor, group, world: int) -> torch.Tensor:
     return out.view((world,) + tuple(t.shape)).to(dev)
 
 
+# Same switches as cyclic_reduction.EAGER_PD_CHECK / RELEASE_FACTORS_AFTER_BACKWARD, for the chunked path: by default the
+# non-positive-definite report is read before the forward call returns and the factors live as long as the graph.
+DEFERRED_PD_CHECK = False
+RELEASE_FACTORS_AFTER_BACKWARD = False
+
+
 class _Ctx:
     pass
 
@@ -108,14 +116,14 @@ def _Side(dev, active):
 
 
 def _finish_check(ctx, keep):
-    """Non-positive-definite reports of the (up to three) sweeps of a forward pass.  Forward-only calls look at
-    them at once (one device->host read).  When a backward pass follows (`keep`), the read is queued
-    asynchronously and looked at by `chunked_backward` after it has queued its own work: a blocking read here
-    would drain the GPU and leave it idle while the host prepares the backward pass (~0.3 ms per step)."""
+    """Non-positive-definite reports of the (up to three) sweeps of a forward pass.  By default they are looked at
+    at once (one device->host read).  With DEFERRED_PD_CHECK and a backward pass to follow (`keep`), the read is
+    queued asynchronously and looked at by `chunked_backward` after it has queued its own work: a blocking read
+    here drains the GPU and leaves it idle while the host prepares the backward pass (~0.3 ms per step)."""
     packs = (ctx.pack, ctx.pack_tail, getattr(ctx, "bpack", None))
     engine = ctx.engine
     Deferred = getattr(engine, "DeferredCheck", None)
-    if keep and Deferred is not None and ctx.shape[2].type == "cuda":
+    if keep and DEFERRED_PD_CHECK and Deferred is not None and ctx.shape[2].type == "cuda":
         ctx.deferred = Deferred(packs)
     else:
         ctx.deferred = None
@@ -238,6 +246,11 @@ def chunked_backward(ctx, g_mahal, g_logdet):
     if ctx.bpack is not None:
         Sbd, Sbo, wb = engine.backward_sweep(ctx.bpack, sigma=True, w=True)
         Sbd, Sbo, wb = Sbd[0], Sbo[0], wb[0]
+    else:
+        # the whole series is shorter than one sub-chunk: no boundary node exists, the tail's left halo is empty
+        Sbd = torch.zeros((1, ell, ell), dtype=dtype, device=dev)
+        Sbo = torch.zeros((0, ell, ell), dtype=dtype, device=dev)
+        wb = torch.zeros((1, ell), dtype=dtype, device=dev)
     g0 = plan.bounds[rank][0]                                       # global index of the first local sub-chunk
     zero_b = torch.zeros((1, ell, ell), dtype=dtype, device=dev)
     zero_v = torch.zeros((1, ell), dtype=dtype, device=dev)
@@ -305,9 +318,10 @@ class ChunkedMahalAndDet(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_mahal, g_det):
         if ctx.c is None:
-            raise RuntimeError("the CR factors were released by the first backward pass (retain_graph is not supported)")
+            raise RuntimeError("the CR factors were released by the first backward pass (RELEASE_FACTORS_AFTER_BACKWARD is set)")
         gR, gO, gx = chunked_backward(ctx.c, g_mahal, g_det)
-        ctx.c = None                                   # release ~3 n l^2 elements of factors now, not at graph teardown
+        if RELEASE_FACTORS_AFTER_BACKWARD:
+            ctx.c = None                               # release ~3 n l^2 elements of factors now, not at graph teardown
         return gR, gO, gx, None, None, None, None
 
 

@@ -96,3 +96,17 @@ def leg_precision_rows(gaps_ext, G, B, LLT, dtype, chunk: int = 1 << 20):
         R[a:b] = (shift + from_prev[:-1] + to_next[1:]).to(dtype)
         Oprev[a:b] = (-(fwd * mask)[:-1]).to(dtype)
     return R, Oprev
+
+
+def x_for_rows(lo: int, hi: int, ell: int, seed: int, device, dtype, block: int = 1 << 20):
+    """Right-hand side rows [lo, hi) of ONE global series, identical whatever the partition: rows are drawn per block
+    of `block` global indices from a generator seeded by (seed, block index) -- the same scheme as `gaps_for_rows`."""
+    out = torch.empty((max(hi - lo, 0), ell), dtype=dtype, device=device)
+    if hi <= lo:
+        return out
+    for blk in range(lo // block, (hi - 1) // block + 1):
+        gen = torch.Generator(device=device).manual_seed(seed * 7919 + blk)
+        vals = torch.randn((block, ell), generator=gen, dtype=torch.float32, device=device)
+        s, e = max(lo, blk * block), min(hi, (blk + 1) * block)
+        out[s - lo:e - lo] = vals[s - blk * block:e - blk * block].to(dtype)
+    return out

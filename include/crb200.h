@@ -3,10 +3,16 @@
  * Drop-in boundary for the hot path of cunningham-lab/cyclic-gps: the module-level
  * functions of cyclic_gps/cyclic_reduction.py (the reference has no FFI; its "interface" is
  * that Python module, imported at cyclic_gps/models.py:10).  Each entry below names the
- * reference code it replaces.  The library allocates nothing, keeps no global state (apart from
- * a diagnostic launch counter), takes
- * raw DEVICE pointers plus a cudaStream_t (as void*), is re-entrant and may be called from any
- * host thread (the autograd engine calls the backward entries from its own thread).
+ * reference code it replaces.  The library allocates nothing and takes raw DEVICE pointers plus a
+ * cudaStream_t (as void*).
+ *
+ * Threading: every entry is re-entrant and may be called from any host thread (the autograd engine calls the
+ * backward entries from its own thread).  The only process-wide state is a diagnostic launch counter and two
+ * per-device caches held in atomics (kernel shared-memory opt-in done, SM count), which are idempotent under
+ * races.  The CURRENT CUDA device of the calling thread must be the device that owns `stream` and the buffers
+ * (the caches and the fused-tail decision are keyed by cudaGetDevice()); torch callers get this from
+ * torch.cuda.device / set_device.  Argument errors (CRB200_EINVAL, CRB200_EUNSUPPORTED) are detected before
+ * anything is launched.
  *
  * Conventions
  *   dtype     CRB200_F32 / CRB200_F64; all arrays of one call share it.

@@ -367,23 +367,47 @@ def test_config2_shape_properties():
 
 
 def test_not_positive_definite_under_autograd():
-    """Forward-only: raised by mahal_and_det itself.  Under autograd the report is read asynchronously and raised by
-    backward() (cyclic_reduction.EAGER_PD_CHECK = True restores the eager check)."""
+    """Default = the reference's contract (cyclic_reduction.py:429): raised inside mahal_and_det, with or without
+    autograd.  EAGER_PD_CHECK = False (opt-in, bench.py) defers the report to backward()."""
     c = cr()
     R, O, x = (t.cuda() for t in leg_inputs(3, 200, torch.float64, seed=9))
     R[77] = -R[77]
     with pytest.raises(c.NotPositiveDefiniteError):
         c.mahal_and_det(R, O, x)
+    with pytest.raises(c.NotPositiveDefiniteError):
+        c.mahal_and_det(R.clone().requires_grad_(True), O, x)
+    c.EAGER_PD_CHECK = False
+    try:
+        Rr = R.clone().requires_grad_(True)
+        mm, dd = c.mahal_and_det(Rr, O, x)
+        with pytest.raises(c.NotPositiveDefiniteError):
+            (mm + dd).backward()
+    finally:
+        c.EAGER_PD_CHECK = True
+
+
+def test_backward_twice_and_release_flag():
+    """backward(retain_graph=True) followed by another backward works like the reference's tape; the opt-in
+    RELEASE_FACTORS_AFTER_BACKWARD frees the factors after the first pass and a second one raises."""
+    c = cr()
+    R, O, x = (t.cuda() for t in leg_inputs(3, 120, torch.float64, seed=4))
     Rr = R.clone().requires_grad_(True)
     mm, dd = c.mahal_and_det(Rr, O, x)
-    with pytest.raises(c.NotPositiveDefiniteError):
-        (mm + dd).backward()
-    c.EAGER_PD_CHECK = True
+    (mm + dd).backward(retain_graph=True)
+    g1 = Rr.grad.clone()
+    Rr.grad = None
+    (mm + dd).backward()
+    assert relerr(Rr.grad, g1) == 0.0
+    (ga,) = torch.autograd.grad(c.mahal_and_det(Rr, O, x)[0], Rr)
+    assert ga.shape == Rr.shape
+    c.RELEASE_FACTORS_AFTER_BACKWARD = True
     try:
-        with pytest.raises(c.NotPositiveDefiniteError):
-            c.mahal_and_det(R.clone().requires_grad_(True), O, x)
+        mm, dd = c.mahal_and_det(Rr, O, x)
+        (mm + dd).backward(retain_graph=True)
+        with pytest.raises(RuntimeError):
+            (mm + dd).backward()
     finally:
-        c.EAGER_PD_CHECK = False
+        c.RELEASE_FACTORS_AFTER_BACKWARD = False
 
 
 @pytest.mark.parametrize("l,n,dtype", [(3, 257, torch.float64), (8, 500, torch.float64), (4, 333, torch.float32)])

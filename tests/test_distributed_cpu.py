@@ -23,7 +23,10 @@ def make_series(n, l, seed):
     g = torch.Generator().manual_seed(seed)
     G, B, LLT = orc.leg_params(l, seed=seed)
     gaps = -torch.log(torch.rand(n - 1, generator=g, dtype=torch.float64)) + 0.05
-    R, O = orc.leg_posterior_precision(gaps, G, B, LLT)
+    if n > 1:
+        R, O = orc.leg_posterior_precision(gaps, G, B, LLT)
+    else:                                   # a single row has no gaps: any SPD block will do
+        R, O = (2.0 * torch.eye(l, dtype=torch.float64) + B.T @ B).unsqueeze(0), torch.zeros((0, l, l), dtype=torch.float64)
     x = torch.randn((n, l), generator=g, dtype=torch.float64)
     Oprev = torch.cat([torch.full((1, l, l), 7.0, dtype=torch.float64), O], dim=0)   # entry 0 must be ignored
     return R, O, Oprev, x
@@ -51,7 +54,8 @@ def run_rank(rank, world, n, l, sub, seed, gm, gd, group=None):
         assert_close(xl.grad, gx[lo:hi], 1e-9, f"gx rank{rank}")
 
 
-@pytest.mark.parametrize("n,l,sub", [(32, 2, 8), (37, 3, 8), (64, 1, 4), (9, 2, 8), (8, 2, 8), (50, 3, 16), (7, 2, 2)])
+@pytest.mark.parametrize("n,l,sub", [(32, 2, 8), (37, 3, 8), (64, 1, 4), (9, 2, 8), (8, 2, 8), (50, 3, 16), (7, 2, 2),
+                                       (5, 2, 8), (1, 2, 2), (3, 1, 4)])   # series shorter than one sub-chunk: tail only
 def test_chunked_single_process(n, l, sub):
     run_rank(0, 1, n, l, sub, seed=n + l, gm=0.7, gd=-1.3)
 
@@ -69,7 +73,8 @@ def _worker(rank, world, port, cases):
 
 
 def test_chunked_two_ranks_gloo():
-    cases = [(64, 2, 8), (77, 3, 8), (40, 2, 4), (19, 2, 8)]
+    cases = [(64, 2, 8), (77, 3, 8), (40, 2, 4), (19, 2, 8),
+             (5, 2, 8), (1, 2, 2), (12, 2, 8)]      # more ranks than sub-chunks: a rank owns nothing / only the ragged tail
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, cases), nprocs=2, join=True)
 
@@ -84,6 +89,10 @@ def test_plan_properties():
     assert hi == 10 ** 8 and p.tail_rows(7) == 10 ** 8 % p.sub
     q = D.make_plan(10 ** 8, 8, sub=1 << 20)
     assert q.nsub == 96 and q.nboundary == 95 and max(b - a for a, b in q.bounds) == 12
+    # more ranks than sub-chunks with a ragged tail: exactly one rank owns the tail, the surplus ranks own nothing
+    t = D.make_plan(20, 4, sub=8)
+    assert [t.rows(r) for r in range(4)] == [(0, 8), (8, 16), (16, 20), (20, 20)]
+    assert [t.full_subchunks(r) for r in range(4)] == [1, 1, 0, 0] and [t.tail_rows(r) for r in range(4)] == [0, 0, 4, 0]
     covered = 0
     for r in range(8):
         a, b = p.rows(r)

@@ -111,8 +111,8 @@ def test_long_series_full_size_properties():
 
 
 def test_chunked_not_positive_definite_is_reported():
-    """Forward-only calls raise at once; under autograd the report of the forward sweeps is read
-    asynchronously and raised by the backward pass (distributed._finish_check)."""
+    """Default: raised by the forward call, with or without autograd.  With distributed.DEFERRED_PD_CHECK the report of
+    the forward sweeps is read asynchronously and raised by the backward pass (distributed._finish_check)."""
     from cyclic_gps import distributed as D
     from cyclic_gps._engine import NotPositiveDefiniteError
     n, l = 3000, 4
@@ -121,7 +121,13 @@ def test_chunked_not_positive_definite_is_reported():
     plan = D.make_plan(n, 1, sub=256)
     with pytest.raises(NotPositiveDefiniteError):
         D.chunked_mahal_and_det(R.cuda(), Oprev.cuda(), x.cuda(), plan, 0)
-    Rl = R.cuda().requires_grad_(True)
-    mh, ld = D.chunked_mahal_and_det(Rl, Oprev.cuda(), x.cuda(), plan, 0)
     with pytest.raises(NotPositiveDefiniteError):
-        (mh + ld).backward()
+        D.chunked_mahal_and_det(R.cuda().requires_grad_(True), Oprev.cuda(), x.cuda(), plan, 0)
+    D.DEFERRED_PD_CHECK = True
+    try:
+        Rl = R.cuda().requires_grad_(True)
+        mh, ld = D.chunked_mahal_and_det(Rl, Oprev.cuda(), x.cuda(), plan, 0)
+        with pytest.raises(NotPositiveDefiniteError):
+            (mh + ld).backward()
+    finally:
+        D.DEFERRED_PD_CHECK = False

@@ -9,7 +9,7 @@ for l, dt in cases:
     s = 4 if dt == "float32" else 8
     rows = int(min(5.12e6, 2.0e9 / (l * l * s)))            # keep inputs + factors around a few GB
     batch = max(8, rows // 10000)
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--ell", str(l), "--dtype", dt, "--batch", str(batch), "--n", "10000",
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--ell", str(l), "--dtype", dt, "--batch", str(batch), "--n", "10000", "--no-long", "--no-strong",
            "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     try:
