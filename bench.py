@@ -312,6 +312,7 @@ def long_parity(rk, ell, dtype, n_par, sub):
     return out
 
 
+@torch.no_grad()
 def long_residual(rk, R, Oprev, x, w, chunk=1 << 22):
     """max |J w - x| / max |x| over ALL rows of the distributed series: every rank needs w of the row before its first
     and after its last row, and the coupling block of the row after its last (one tiny all-gather)."""
