@@ -52,7 +52,7 @@ def kernel_family(ell, s):
     """Which kernel family libcrb200 dispatches to."""
     if s * ell * ell <= 400:
         return "tpn"                       # thread-per-node (CRB200_TPN_MAX_BLOCK_BYTES)
-    return "cs" if (s == 8 and ell == 8) else "level"
+    return "cs" if (s == 8 and ell == 8) else "mma"    # column-split / warp-per-node DMMA
 
 
 def peaks():
@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--long-dtype", default="float32")
     ap.add_argument("--parity-n", type=int, default=4_000_000)
     ap.add_argument("--sub", type=int, default=None, help="long workload: rows per sub-chunk (power of two)")
-    ap.add_argument("--variant", type=int, default=0, help="force a kernel family (0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split)")
+    ap.add_argument("--variant", type=int, default=0, help="force a kernel family (0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split, 4 warp-per-node DMMA)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

@@ -12,6 +12,13 @@
 #define CRB_HAVE_TPN 0
 #endif
 #include "cr_halfsolve.cuh"
+#if CRB_HI >= 8   // warp-per-node DMMA kernels: blocks that do not fit one thread's registers (and ell = 8 for comparison)
+#include "cr_mma_fwd.cuh"
+#include "cr_mma_bwd.cuh"
+#define CRB_HAVE_MMA 1
+#else
+#define CRB_HAVE_MMA 0
+#endif
 #if !CRB_HAVE_TPN
 #include "cr_tpn_common.cuh"   // MultiArgs
 #endif
@@ -44,8 +51,24 @@ struct CsSel {
 
 template <int L>
 struct Dispatch {
+  // the warp-per-node DMMA family is the automatic choice wherever neither the thread-per-node nor the column-split family exists
+  static constexpr bool kMma = CRB_HAVE_MMA && (L >= 8);
+  static constexpr bool kSmallFamilies =
+#if CRB_HAVE_TPN
+      TpnFwdCfg<CRB_T, L>::ELIGIBLE || CsSel<L>::FWD;
+#else
+      false;
+#endif
   static cudaError_t fwd(int ell, const LevelFwdArgs& a, cudaStream_t s) {
     if (ell == L) {
+#if CRB_HAVE_MMA
+      if constexpr (kMma) {
+        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies)) return launch_mma_fwd<CRB_T, L>(a, s);
+      } else
+#endif
+      {
+        if (a.variant == CRB200_MMA) return cudaErrorInvalidValue;
+      }
 #if CRB_HAVE_TPN
       if constexpr (CsSel<L>::FWD) {
         // auto: column-split only where the thread-per-node kernel does not exist (measured: at fp32 l=8 the
@@ -68,6 +91,14 @@ struct Dispatch {
   }
   static cudaError_t bwd(int ell, const LevelBwdArgs& a, cudaStream_t s) {
     if (ell == L) {
+#if CRB_HAVE_MMA
+      if constexpr (kMma) {
+        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies)) return launch_mma_bwd<CRB_T, L>(a, s);
+      } else
+#endif
+      {
+        if (a.variant == CRB200_MMA) return cudaErrorInvalidValue;
+      }
 #if CRB_HAVE_TPN
       if constexpr (CsSel<L>::BWD) {
         if (a.variant == CRB200_COLUMN_SPLIT || (a.variant == CRB200_AUTO && !TpnBwdCfg<CRB_T, L>::ELIGIBLE))
@@ -111,6 +142,9 @@ struct Dispatch {
     if (TpnFwdCfg<CRB_T, L>::ELIGIBLE) return TpnFwdCfg<CRB_T, L>::OWN;
     if (CsSel<L>::FWD) return CsFwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::OWN;
 #endif
+#if CRB_HAVE_MMA
+    if (kMma) return MmaFwdCfg<CRB_T, L>::OWN;
+#endif
     return FwdCfg<CRB_T, L>::NG - 1;
   }
   static int bwd_tile(int ell) {
@@ -118,6 +152,9 @@ struct Dispatch {
 #if CRB_HAVE_TPN
     if (TpnBwdCfg<CRB_T, L>::ELIGIBLE) return TpnBwdCfg<CRB_T, L>::NT;
     if (CsSel<L>::BWD) return CsBwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::NT;
+#endif
+#if CRB_HAVE_MMA
+    if (kMma) return MmaBwdCfg<CRB_T, L>::NT;
 #endif
     return BwdCfg<CRB_T, L>::NG;
   }

@@ -1,0 +1,293 @@
+// Large-block backward level kernel: one WARP per even node, block products on the FP64 tensor path (DMMA).
+//
+// Same contract as cr_level_bwd_kernel (cr_level_bwd.cuh: back-half-solve + selected inverse + optional gradient
+// assembly; reference cyclic_gps/cyclic_reduction.py:362-373, :478-501).  Per even node e, with Di = D_e^{-1}:
+//   P = F_e Di ; Q = G_{e-1} Di                                             DMMA, skipping the zero half of Di
+//   w_{2e}          = Di^T x_e - P^T w~_e - Q^T w~_{e-1}
+//   N1 = S~_d[e] P + S~_o[e-1] Q               Sigma_{2e+1,2e} = -N1        DMMA
+//   N2 = Q^T S~_d[e-1]^T + P^T S~_o[e-1]       Sigma_{2e,2e-1} = -N2        DMMA
+//   Sigma_{2e,2e}   = Di^T Di + P^T N1 + Q^T N2^T                           DMMA, lower tiles only, then mirrored
+// Shared memory per node: five padded blocks of doubles, reused as their first content dies:
+//   T0: D -> Di -> N1     T1: F -> P (-> mirror scratch)     T2: G -> Q     T3: S~_d[e] (read by the right neighbour)
+//   T4: S~_o[e-1] -> N2
+// The three results leave straight from the accumulator fragments (with the gradient transform applied on the way at
+// the top level); the odd rows (S~_d[e], w~_e) are copied through from shared memory.  A CTA is W warps = W
+// consecutive even nodes; the only data shared between warps are S~_d[e-1] and w~_{e-1}, read from the left
+// neighbour's record after ONE __syncthreads that follows the stage-in (warp 0 stages its own copy).
+#pragma once
+#include "cr_level_bwd.cuh"
+#include "cr_mma_common.cuh"
+
+namespace crb200 {
+
+template <typename T, int L>
+struct MmaBwdCfg {
+  using Geo = MmaGeom<L>;
+  static constexpr bool ELIGIBLE = (L >= 8);
+  static constexpr int LP = Geo::LP, LD = Geo::LD, BLK = Geo::BLK;
+  static constexpr int VEC = 4 * LP;                          // x_e | w~_e | w_{2e} | spare
+  static constexpr int REC = 5 * BLK + VEC;                   // doubles per node
+  static constexpr int LEFT = BLK + VEC;                      // record of the left neighbour of warp 0: S~_d[e0-1], w~_{e0-1}
+  static constexpr int W = LP <= 24 ? 8 : 4;                  // warps (= nodes) per CTA
+  static constexpr int NT = W;
+  static constexpr size_t SMEM = (size_t)(LEFT + W * REC) * sizeof(double);
+  static constexpr int MIN_CTAS = (2 * (SMEM + 1024) <= 227 * 1024) ? 2 : 1;
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(32 * MmaBwdCfg<T, L>::W, MmaBwdCfg<T, L>::MIN_CTAS)
+cr_mma_bwd_kernel(const LevelBwdArgs a) {
+  using C = MmaBwdCfg<T, L>;
+  constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NT = C::NT, NTL = LP / 8, BS = L * L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* base = reinterpret_cast<double*>(smem_raw);
+  double* N = base + C::LEFT + (size_t)warp * C::REC;
+  double* T0 = N;
+  double* T1 = N + BLK;
+  double* T2 = N + 2 * BLK;
+  double* T3 = N + 3 * BLK;
+  double* T4 = N + 4 * BLK;
+  double* X = N + 5 * BLK;
+  double* WT = X + LP;
+  double* WV = WT + LP;
+  // left neighbour: S~_d[e-1], w~_{e-1}
+  const double* LSD = warp == 0 ? base : (N - C::REC + 3 * BLK);
+  const double* LWT = warp == 0 ? base + BLK : (N - C::REC + 5 * BLK + LP);
+
+  const int m = a.m;
+  const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
+  const int tiles = (E + NT - 1) / NT;
+  const int b = blockIdx.x / tiles;
+  const int tile = blockIdx.x - b * tiles;
+  const int e0 = tile * NT;
+  const int e = e0 + warp;
+  const bool do_sigma = a.Sd_out != nullptr;
+  const bool do_w = a.w_out != nullptr;
+  const bool halo = a.G_halo != nullptr;
+  const bool valid = e < E;
+  const bool has_odd = valid && e < o;
+  const bool has_left = valid && (e >= 1 || halo);
+  const bool has_so = has_left && has_odd;
+  const bool grad = a.grad_mode != 0;
+  double gm = 0.0, gd = 1.0;
+  if (grad) {
+    gm = a.gm != nullptr ? a.gm[b] : 0.0;
+    gd = a.gd != nullptr ? a.gd[b] : 0.0;
+  }
+
+  // ---------------- stage in ----------------
+  if (valid) {
+    mma_pad_block<L, LP>(T0, true, lane);
+    mma_stage_block<T, L, LP>(T0, static_cast<const T*>(a.D) + ((size_t)b * E + e) * BS, lane, is_aligned16(a.D));
+  } else {
+    mma_fill_block<LP>(T0, true, lane);
+  }
+  if (has_odd) {
+    mma_pad_block<L, LP>(T1, false, lane);
+    mma_stage_block<T, L, LP>(T1, static_cast<const T*>(a.F) + ((size_t)b * o + e) * BS, lane, is_aligned16(a.F));
+  } else {
+    mma_fill_block<LP>(T1, false, lane);
+  }
+  if (has_left) {
+    mma_pad_block<L, LP>(T2, false, lane);
+    if (e >= 1) mma_stage_block<T, L, LP>(T2, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e - 1)) * BS, lane, is_aligned16(a.G));
+    else mma_stage_block<T, L, LP>(T2, static_cast<const T*>(a.G_halo) + (size_t)b * BS, lane, is_aligned16(a.G_halo));
+  } else {
+    mma_fill_block<LP>(T2, false, lane);
+  }
+  if (do_sigma) {
+    if (has_odd) {
+      mma_pad_block<L, LP>(T3, false, lane);
+      mma_stage_block<T, L, LP>(T3, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + e) * BS, lane, is_aligned16(a.Sd_in));
+    } else {
+      mma_fill_block<LP>(T3, false, lane);
+    }
+    if (has_so) {
+      mma_pad_block<L, LP>(T4, false, lane);
+      if (e >= 1) mma_stage_block<T, L, LP>(T4, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e - 1)) * BS, lane, is_aligned16(a.So_in));
+      else mma_stage_block<T, L, LP>(T4, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, lane, is_aligned16(a.So_halo_in));
+    } else {
+      mma_fill_block<LP>(T4, false, lane);
+    }
+    if (warp == 0) {
+      double* lsd = base;
+      if (e0 >= 1) {
+        mma_pad_block<L, LP>(lsd, false, lane);
+        mma_stage_block<T, L, LP>(lsd, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1)) * BS, lane, is_aligned16(a.Sd_in));
+      } else if (halo) {
+        mma_pad_block<L, LP>(lsd, false, lane);
+        mma_stage_block<T, L, LP>(lsd, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, lane, is_aligned16(a.Sd_halo));
+      } else {
+        mma_fill_block<LP>(lsd, false, lane);
+      }
+    }
+  }
+  if (lane < LP) {
+    const bool in = lane < L;
+    X[lane] = (do_w && valid && in) ? (double)static_cast<const T*>(a.xk)[((size_t)b * E + e) * L + lane] : 0.0;
+    WT[lane] = (do_w && has_odd && in) ? (double)static_cast<const T*>(a.w_in)[((size_t)b * o + e) * L + lane] : 0.0;
+    WV[lane] = 0.0;
+    if (warp == 0) {
+      double v = 0.0;
+      if (do_w && in) {
+        if (e0 >= 1) v = (double)static_cast<const T*>(a.w_in)[((size_t)b * o + (e0 - 1)) * L + lane];
+        else if (halo) v = (double)static_cast<const T*>(a.w_halo)[(size_t)b * L + lane];
+      }
+      base[BLK + lane] = v;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();                                      // the left neighbour's S~_d and w~ are visible
+
+  // ---------------- Di, P, Q, w ----------------
+  {
+    double invd[LP];
+    const int r = lane < LP ? lane : 0;
+    const double mine = 1.0 / T0[r * LD + r];
+#pragma unroll
+    for (int j = 0; j < LP; ++j) invd[j] = __shfl_sync(0xffffffffu, mine, j);
+    warp_tri_inverse<LP>(T0, invd, lane);               // T0 = Di
+  }
+  double acc[NTL][NTL][2];
+  if (has_odd) {
+    acc_zero<LP>(acc);
+    warp_gemm<LP, false, false, K_GE_N, false>(acc, T1, T0, lane);         // P = F Di
+    __syncwarp();
+    acc_to_smem<LP>(T1, acc, 1.0, lane);
+  }
+  if (has_left) {
+    acc_zero<LP>(acc);
+    warp_gemm<LP, false, false, K_GE_N, false>(acc, T2, T0, lane);         // Q = G Di
+    __syncwarp();
+    acc_to_smem<LP>(T2, acc, 1.0, lane);
+  }
+  __syncwarp();
+  double wv = 0.0;
+  if (do_w) {
+    wv = warp_matvec<LP, true>(T0, X, lane);                               // Di^T x_e
+    if (has_odd) wv -= warp_matvec<LP, true>(T1, WT, lane);                // - P^T w~_e
+    if (has_left) wv -= warp_matvec<LP, true>(T2, LWT, lane);              // - Q^T w~_{e-1}
+    if (lane < LP) WV[lane] = wv;
+    __syncwarp();
+  }
+
+  const int lr = lane >> 2, lc = lane & 3;
+  if (do_sigma) {
+    T* const gSd = static_cast<T*>(a.Sd_out) + (size_t)b * a.strideSd;
+    T* const gSo = a.So_out != nullptr ? static_cast<T*>(a.So_out) + (size_t)b * a.strideSo : nullptr;
+    const bool vSd = is_aligned16(gSd), vSo = is_aligned16(gSo);
+    double accE[NTL][NTL][2];
+    acc_zero<LP>(accE);
+    if (valid) warp_gemm<LP, true, false, K_GE_MAX_MN, true>(accE, T0, T0, lane);     // Di^T Di (lower tiles)
+    __syncwarp();                                         // Di is dead: T0 may take N1
+    // N1 = S~_d[e] P + S~_o[e-1] Q ;  Sigma_{2e+1,2e} = -N1  -> So_out row 2e
+    if (has_odd) {
+      acc_zero<LP>(acc);
+      warp_gemm<LP, false, false, K_FULL, false>(acc, T3, T1, lane);
+      if (has_so) warp_gemm<LP, false, false, K_FULL, false>(acc, T4, T2, lane);
+      acc_to_smem<LP>(T0, acc, 1.0, lane);
+      T* dst = gSo + (size_t)(2 * e) * BS;
+#pragma unroll
+      for (int mt = 0; mt < NTL; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) {
+          const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
+          double v0 = -acc[mt][nt][0], v1 = -acc[mt][nt][1];
+          if (grad) {     // gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T)
+            const double wr = WT[row];
+            v0 = 2.0 * (gd * v0 - gm * wr * WV[col]);
+            v1 = 2.0 * (gd * v1 - gm * wr * WV[col + 1]);
+          }
+          frag_pair_store<T, L>(dst, row, col, v0, v1, vSo);
+        }
+    } else {
+      mma_fill_block<LP>(T0, false, lane);
+    }
+    // N2 = Q^T S~_d[e-1]^T + P^T S~_o[e-1] ;  Sigma_{2e,2e-1} = -N2  -> So_out row 2e-1 (or the halo block)
+    if (has_left) {
+      acc_zero<LP>(acc);
+      warp_gemm<LP, true, true, K_FULL, false>(acc, T2, LSD, lane);
+      if (has_so) warp_gemm<LP, true, false, K_FULL, false>(acc, T1, T4, lane);
+      __syncwarp();                                       // S~_o[e-1] has been read by every lane
+      acc_to_smem<LP>(T4, acc, 1.0, lane);
+      T* dst = e >= 1 ? (gSo != nullptr ? gSo + (size_t)(2 * e - 1) * BS : nullptr)
+                      : (a.So_halo_out != nullptr ? static_cast<T*>(a.So_halo_out) + (size_t)b * BS : nullptr);
+      if (dst != nullptr) {
+        const bool vec = e >= 1 ? vSo : is_aligned16(a.So_halo_out);
+#pragma unroll
+        for (int mt = 0; mt < NTL; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) {
+            const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
+            double v0 = -acc[mt][nt][0], v1 = -acc[mt][nt][1];
+            if (grad) {   // gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)
+              const double wr = WV[row];
+              v0 = 2.0 * (gd * v0 - gm * wr * LWT[col]);
+              v1 = 2.0 * (gd * v1 - gm * wr * LWT[col + 1]);
+            }
+            frag_pair_store<T, L>(dst, row, col, v0, v1, vec);
+          }
+      }
+    } else {
+      mma_fill_block<LP>(T4, false, lane);
+    }
+    __syncwarp();
+    // Sigma_{2e,2e} = Di^T Di + P^T N1 + Q^T N2^T  (lower tiles), mirrored through T1, -> Sd_out row 2e
+    if (valid) {
+      if (has_odd) warp_gemm<LP, true, false, K_FULL, true>(accE, T1, T0, lane);
+      if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
+      __syncwarp();                                       // P is dead: T1 is the mirror scratch
+      acc_to_smem<LP>(T1, accE, 1.0, lane);
+      __syncwarp();
+      acc_mirror_from_smem<LP>(accE, T1, 1.0, lane);
+      T* dst = gSd + (size_t)(2 * e) * BS;
+#pragma unroll
+      for (int mt = 0; mt < NTL; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) {
+          const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
+          double v0 = accE[mt][nt][0], v1 = accE[mt][nt][1];
+          if (grad) {     // gR_{2e} = gd Sigma_{2e,2e} - gm w_{2e} w_{2e}^T
+            const double wr = WV[row];
+            v0 = gd * v0 - gm * wr * WV[col];
+            v1 = gd * v1 - gm * wr * WV[col + 1];
+          }
+          frag_pair_store<T, L>(dst, row, col, v0, v1, vSd);
+        }
+    }
+    // odd row copied through: Sigma_{2e+1,2e+1} = S~_d[e]   (gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T)
+    if (has_odd) {
+      T* dst = gSd + (size_t)(2 * e + 1) * BS;
+      if (grad) {
+        const double* wt = WT;
+        const double gdl = gd, gml = gm;
+        mma_store_block_f<T, L, LP>(dst, T3, lane, vSd, [=](int r, int c, double v) { return gdl * v - gml * wt[r] * wt[c]; });
+      } else {
+        mma_store_block<T, L, LP>(dst, T3, lane, vSd);
+      }
+    }
+  }
+  if (do_w && lane < L) {
+    T* gW = static_cast<T*>(a.w_out) + (size_t)b * a.stridew;
+    const double sc = grad ? 2.0 * gm : 1.0;                // gx = 2 gm w
+    if (valid) gW[(size_t)(2 * e) * L + lane] = (T)(sc * wv);
+    if (has_odd) gW[(size_t)(2 * e + 1) * L + lane] = (T)(sc * WT[lane]);
+  }
+}
+
+template <typename T, int L>
+cudaError_t launch_mma_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
+  using C = MmaBwdCfg<T, L>;
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_mma_bwd_kernel<T, L>, (int)C::SMEM, attr_done); e != cudaSuccess) return e;
+  const int E = (a.m + 1) / 2;
+  const long long tiles = (E + C::NT - 1) / C::NT;
+  const long long grid = tiles * a.batch;
+  if (grid <= 0) return cudaSuccess;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  cr_mma_bwd_kernel<T, L><<<(unsigned)grid, 32 * C::W, C::SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace crb200

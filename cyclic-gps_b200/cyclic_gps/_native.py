@@ -172,7 +172,7 @@ def _fill(struct, fields):
     return struct
 
 
-# Kernel family override for tests / benchmarks: 0 auto, 1 lane-per-row, 2 thread-per-node.
+# Kernel family override for tests / benchmarks: 0 auto, 1 lane-per-row, 2 thread-per-node, 3 column-split, 4 warp-per-node DMMA.
 VARIANT = int(os.environ.get("CRB200_VARIANT", "0"))
 
 # Optional launch tracer (bench.py): an object with begin(kind, dtype, ell, batch, m) -> token

@@ -36,12 +36,15 @@ extern "C" {
 #define CRB200_F32 0
 #define CRB200_F64 1
 
-/* kernel families: lane-per-row (any ell <= 32), thread-per-node (sizeof(T)*ell*ell <= 400 B: fp32 ell <= 10, fp64 ell <= 7) and
- * column-split (several lanes per node: fp32 ell=8, fp64 ell=4 and 8; chosen automatically for fp64 ell=8) */
+/* kernel families: thread-per-node (sizeof(T)*ell*ell <= 400 B: fp32 ell <= 10, fp64 ell <= 7), column-split (several lanes
+ * per node: fp32 ell=8, fp64 ell=4 and 8; chosen automatically for fp64 ell=8), warp-per-node with the block products on the
+ * FP64 tensor path (DMMA; ell >= 8, chosen automatically for every larger block: fp32 ell >= 11, fp64 ell >= 9; fp32 data is
+ * widened to fp64 on chip) and the first-generation lane-per-row kernels (any ell <= 32; kept as a cross-check) */
 #define CRB200_AUTO 0
 #define CRB200_LANE_PER_ROW 1
 #define CRB200_THREAD_PER_NODE 2
 #define CRB200_COLUMN_SPLIT 3
+#define CRB200_MMA 4
 #define CRB200_COPY_ONLY 99       /* profiling aid (thread-per-node kernels): stage in / out only, results are garbage */
 
 #define CRB200_OK 0

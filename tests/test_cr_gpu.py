@@ -177,9 +177,16 @@ def test_full_path_vs_oracle(l, n, dtype):
     (4, 3001, torch.float32, 1), (4, 3001, torch.float32, 2),
     (3, 500, torch.float64, 1), (3, 500, torch.float64, 2), (5, 300, torch.float32, 1), (5, 300, torch.float32, 2),
     (9, 700, torch.float32, 1), (9, 700, torch.float32, 2), (10, 700, torch.float32, 1), (10, 700, torch.float32, 2),   # upper end of thread-per-node
-    (6, 700, torch.float64, 1), (6, 700, torch.float64, 2), (7, 700, torch.float64, 1), (7, 700, torch.float64, 2)])
+    (6, 700, torch.float64, 1), (6, 700, torch.float64, 2), (7, 700, torch.float64, 1), (7, 700, torch.float64, 2),
+    # warp-per-node DMMA family (variant 4): every padded size 8 / 16 / 24 / 32, odd sizes, both storage types;
+    # lane-per-row (variant 1) kept as the cross-check at the same sizes
+    (8, 700, torch.float32, 4), (8, 700, torch.float64, 4), (9, 300, torch.float64, 4), (11, 333, torch.float32, 4),
+    (12, 500, torch.float64, 4), (13, 301, torch.float64, 4), (16, 1100, torch.float64, 4), (16, 1100, torch.float32, 4),
+    (17, 260, torch.float32, 4), (21, 200, torch.float64, 4), (24, 300, torch.float64, 4), (24, 300, torch.float32, 4),
+    (27, 130, torch.float32, 4), (31, 150, torch.float64, 4), (32, 260, torch.float64, 4), (32, 260, torch.float32, 4),
+    (16, 300, torch.float64, 1), (32, 100, torch.float32, 1)])
 def test_every_kernel_family_vs_oracle(l, n, dtype, variant):
-    """The same contract is implemented by up to three kernel families (include/crb200.h, `variant`);
+    """The same contract is implemented by up to four kernel families (include/crb200.h, `variant`);
     force each one and compare the whole path (forward, backward, selected inverse, solve) with the oracle."""
     from cyclic_gps import _native
     c = cr()

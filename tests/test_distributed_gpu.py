@@ -59,7 +59,8 @@ def _run(rank, world, n, l, dtype, sub, group=None, variant=0):
     (5000, 4, torch.float32, 256, 0), (4096, 8, torch.float32, 512, 0), (3001, 3, torch.float64, 128, 0),
     (2050, 2, torch.float64, 64, 0), (1000, 8, torch.float64, 64, 0), (777, 16, torch.float64, 32, 0),
     (3001, 3, torch.float64, 128, 1), (1500, 8, torch.float32, 128, 1), (1500, 8, torch.float32, 128, 3),
-    (1000, 8, torch.float64, 64, 1), (2050, 4, torch.float64, 64, 3)])
+    (1000, 8, torch.float64, 64, 1), (2050, 4, torch.float64, 64, 3),
+    (520, 24, torch.float32, 32, 0), (300, 13, torch.float64, 16, 0), (400, 32, torch.float64, 32, 4), (900, 8, torch.float32, 64, 4)])
 def test_chunked_world1(n, l, dtype, sub, variant):
     _run(0, 1, n, l, dtype, sub, variant=variant)
 
