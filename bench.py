@@ -52,7 +52,9 @@ def kernel_family(ell, s):
     """Which kernel family libcrb200 dispatches to."""
     if s * ell * ell <= 400:
         return "tpn"                       # thread-per-node (CRB200_TPN_MAX_BLOCK_BYTES)
-    return "cs" if (s == 8 and ell == 8) else "mma"    # column-split / warp-per-node DMMA
+    if s == 8 and ell == 8:
+        return "cs"                        # column-split
+    return "mma" if (ell >= 10 if s == 8 else ell >= 17) else "level"    # warp-per-node DMMA / lane-per-row (cr_inst.cu kMmaAuto)
 
 
 def peaks():
@@ -460,6 +462,133 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def bench_model(ell, dtype, dev, train):
+    """A LEGFamily whose matrices equal synth.leg_params(ell, seed=0) -- the model behind the synthetic blocks."""
+    from cyclic_gps.models import LEGFamily
+    from cyclic_gps.synth import leg_params
+    G, Bm, LLT = leg_params(ell, seed=0)
+    model = LEGFamily(rank=ell, obs_dim=1, train=train, data_type=dtype)
+    Rm = torch.tril(0.5 * (G - G.T), diagonal=-1)                     # G = I + Rm - Rm^T + 1e-5 I
+    with torch.no_grad():
+        model.R_params.copy_(Rm[model.R_idxs].to(dtype))
+    model.register_model_matrices_from_params()
+    return model
+
+
+def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
+    """e2e: the headline metric (mahal_and_det forward + backward to gR, gO, gx) fed from host-resident time stamps and
+    observations through the public API; train: the whole LEGFamily.log_likelihood step (two factorisations, gradient
+    wrt the model parameters), also from host buffers."""
+    dev, dist = rk.dev, rk.dist
+    s = torch.empty((), dtype=dtype).element_size()
+    gen = torch.Generator(device=dev).manual_seed(1000 + rk.rank)      # the same gaps as make_inputs
+    gaps = -torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64, device=dev)) + 0.01
+    ts = torch.cat([torch.zeros((B, 1), dtype=torch.float64, device=dev), torch.cumsum(gaps, dim=1)], dim=1)
+    xs = torch.randn((B, n, 1), generator=gen, dtype=dtype, device=dev)
+    h_ts = torch.empty(ts.shape, dtype=torch.float64, pin_memory=True).copy_(ts)
+    h_xs = torch.empty(xs.shape, dtype=dtype, pin_memory=True).copy_(xs)
+    hout = torch.empty((2, B), dtype=dtype, pin_memory=True)
+    d_ts, d_xs = torch.empty_like(ts), torch.empty_like(xs)
+    del gaps, ts, xs
+    model = bench_model(ell, dtype, dev, train=False)
+    _, shift = model._obs_terms()
+    rows = B * n * rk.world
+
+    # builder check: the device-built blocks of series 0 against the fp64 torch construction used for the timed inputs
+    with torch.no_grad():
+        Rb, Ob = model._precision_blocks(h_ts[:1].to(dev), shift)
+        chk = max(float((Rb[0] - R_dev[0]).abs().max() / R_dev[0].abs().max()), float((Ob[0] - O_dev[0]).abs().max() / O_dev[0].abs().max()))
+        del Rb, Ob
+
+    copy_stream = torch.cuda.Stream(device=dev)
+    nchunk = 4 if (B % 4 == 0 and B >= 64) else 1
+    bsz = B // nchunk
+
+    def e2e_step():
+        """The batch is cut into chunks of series: chunk c + 1 crosses PCIe on a copy stream while chunk c is built and reduced."""
+        main_s = torch.cuda.current_stream()
+        copy_stream.wait_stream(main_s)                   # the previous step is done with the device buffers
+        ready = []
+        with torch.cuda.stream(copy_stream):
+            for c in range(nchunk):
+                sl = slice(c * bsz, (c + 1) * bsz)
+                d_ts[sl].copy_(h_ts[sl], non_blocking=True)
+                d_xs[sl].copy_(h_xs[sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
+        tot = torch.zeros((), dtype=torch.float64, device=dev)
+        for c in range(nchunk):
+            sl = slice(c * bsz, (c + 1) * bsz)
+            main_s.wait_event(ready[c])
+            with torch.no_grad():
+                Rs, Os = model._precision_blocks(d_ts[sl], shift)
+                v = model.compute_v(d_xs[sl])
+            Rs.requires_grad_(True); Os.requires_grad_(True); v.requires_grad_(True)
+            mm, dd = cr.mahal_and_det(Rs, Os, v)
+            ll = -0.5 * (mm.double().sum() + dd.double().sum())
+            ll.backward()
+            tot += ll.detach()
+            hout[0, sl].copy_(mm.detach(), non_blocking=True)
+            hout[1, sl].copy_(dd.detach(), non_blocking=True)
+        if dist is not None:
+            dist.all_reduce(tot)
+        main_s.synchronize()                              # the caller holds the result on the host
+        return hout
+
+    def timed(fn, k):
+        fn(); fn()
+        rk.sync()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(k):
+            fn()
+        a1.record()
+        rk.sync()
+        return rk.max_over_ranks(a0.elapsed_time(a1) / k)
+
+    k2 = max(3, min(args.steps, 5))
+    ms2 = timed(e2e_step, k2)
+    h2d = h_ts.numel() * 8 + h_xs.numel() * s
+    e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
+           "ms_per_step": ms2, "steps": k2,
+           "pipeline": f"{nchunk} chunks of {bsz} series, H2D on a copy stream under the compute of the previous chunk; "
+                       "pinned host time stamps (fp64) + observations -> device; precision blocks built on the device "
+                       "(crb200_peg_precision_fwd = the reference's compute_posterior_precision); cr.mahal_and_det + backward to gR, gO, gx; "
+                       "per-series scalars -> host",
+           "builder_vs_fp64_torch_blocks_rel": chk}
+
+    # the whole training step of the reference (LEGFamily.log_likelihood: prior log-det + posterior mahal / log-det,
+    # gradient wrt N, R, B, Lambda) from the same host buffers
+    tmodel = bench_model(ell, dtype, dev, train=True)
+    hgrad = torch.empty(tmodel.parameter_count, dtype=dtype, pin_memory=True)
+
+    def train_step():
+        d_ts.copy_(h_ts, non_blocking=True)
+        d_xs.copy_(h_xs, non_blocking=True)
+        for p in tmodel.parameters():
+            p.grad = None
+        ll = tmodel.log_likelihood(d_ts, d_xs).sum()
+        ll.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in tmodel.parameters()])
+        if dist is not None:
+            flat = flat.to(dev)
+            dist.all_reduce(flat)
+        hgrad.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return ll
+
+    try:
+        ms3 = timed(train_step, k2)
+        train = {"what": "LEGFamily.log_likelihood(ts, xs).sum().backward(): two CR factorisations + device precision builder with "
+                         "its own backward, gradient of the log-likelihood wrt the model parameters", "ms_per_step": ms3,
+                 "value": rows / (ms3 * 1e-3), "unit": UNIT, "parameters": int(tmodel.parameter_count),
+                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hgrad.numel() * s}
+    except Exception as ex:  # noqa: BLE001
+        train = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    return e2e, train
+
+
 def time_batch(rk, cr, tensors, steps, warmup):
     """K timed loglik+grad steps over this rank's series; returns (ms max over ranks, step fn, checksum, launches)."""
     from cyclic_gps import _native
@@ -594,65 +723,12 @@ def main():
                       "value": B * n * args.steps / (ms_s * 1e-3), "unit": UNIT}
             del sub_t
 
-    # ---- end to end: host buffers in, scalars out, copies inside the timed region
-    e2e = None
+    # ---- end to end: HOST buffers in (time stamps + observations), per-series scalars out, copies inside the timed region.
+    # The precision blocks are built ON the device from the time stamps (cyclic_gps.peg, the reference's
+    # compute_posterior_precision), so 12 bytes per row cross PCIe instead of (2 l^2 + l) elements.
+    e2e = train = None
     if not args.no_e2e:
-        hR = torch.empty(R.shape, dtype=dtype, pin_memory=True).copy_(R.detach())
-        hO = torch.empty(O.shape, dtype=dtype, pin_memory=True).copy_(O.detach())
-        hx = torch.empty(x.shape, dtype=dtype, pin_memory=True).copy_(x.detach())
-        hout = torch.empty((2, B), dtype=dtype, pin_memory=True)
-        dR, dO, dx = torch.empty_like(R), torch.empty_like(O), torch.empty_like(x)
-
-        copy_stream = torch.cuda.Stream(device=dev)
-        nchunk = 8 if B % 8 == 0 and B >= 64 else 1
-        bsz = B // nchunk
-
-        def e2e_step():
-            """Host buffers in, per-series scalars out, through the public API (cr.mahal_and_det + backward).
-            The batch is cut into chunks of series; chunk c+1 crosses PCIe on a copy stream while chunk c computes."""
-            main_s = torch.cuda.current_stream()
-            copy_stream.wait_stream(main_s)               # previous step is done with the device buffers
-            ready = []
-            with torch.cuda.stream(copy_stream):
-                for c in range(nchunk):
-                    sl = slice(c * bsz, (c + 1) * bsz)
-                    dR[sl].copy_(hR[sl], non_blocking=True)
-                    dO[sl].copy_(hO[sl], non_blocking=True)
-                    dx[sl].copy_(hx[sl], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    ready.append(ev)
-            tot = torch.zeros((), dtype=torch.float64, device=dev)
-            for c in range(nchunk):
-                sl = slice(c * bsz, (c + 1) * bsz)
-                main_s.wait_event(ready[c])
-                Rc, Oc, xc = (t[sl].detach().requires_grad_(True) for t in (dR, dO, dx))
-                mm, dd = cr.mahal_and_det(Rc, Oc, xc)
-                ll = -0.5 * (mm.double().sum() + dd.double().sum())
-                ll.backward()
-                tot += ll.detach()
-                hout[0, sl].copy_(mm.detach(), non_blocking=True)
-                hout[1, sl].copy_(dd.detach(), non_blocking=True)
-            if dist is not None:
-                dist.all_reduce(tot)
-            main_s.synchronize()                          # the caller holds the result on the host
-            return hout
-
-        e2e_step()
-        rk.sync()
-        k2 = max(3, min(args.steps, 5))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(k2):
-            e2e_step()
-        a1.record()
-        rk.sync()
-        ms2 = rk.max_over_ranks(a0.elapsed_time(a1) / k2)
-        h2d = (hR.numel() + hO.numel() + hx.numel()) * s
-        e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
-               "ms_per_step": ms2, "steps": k2, "pipeline": f"{nchunk} chunks of {bsz} series, H2D on a copy stream overlapped with compute",
-               "h2d_gbs": h2d / (ms2 * 1e-3) / 1e9}
-        del hR, hO, hx, dR, dO, dx
+        e2e, train = run_e2e(args, rk, cr, B, n, ell, dtype, R, O)
 
     # ---- configs[3]: the single long series over the same ranks
     del R, O, x, Rr, Or, xr, step
@@ -717,7 +793,7 @@ def main():
             "config": batch_config(B, n, ell, args.dtype, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches,
             "gpu_launches_per_step": timed_launches // max(args.steps, 1), "per_level_table_launches_per_step": launches_per_step, "clocks": clk,
-            "loglik_checksum": checksum, "strong": strong, "long_series": long_series}
+            "loglik_checksum": checksum, "strong": strong, "train_step": train, "long_series": long_series}
     emit(line)
     rk.close()
 

@@ -86,11 +86,33 @@ def cfg1(reps):
         w = torch.cholesky_solve(x.reshape(-1, 1), Lc).reshape(n, l)
         return 2 * torch.log(torch.diagonal(Lc)).sum(), (x * w).sum(), w
 
+    from cyclic_gps.graphs import GraphedMahalAndDet
+
+    def loglik_grad_eager():
+        Rr, Or, xr = Rg.detach().requires_grad_(True), Og.detach().requires_grad_(True), xg.detach().requires_grad_(True)
+        mm, dd = cr.mahal_and_det(Rr, Or, xr)
+        (mm + dd).backward()
+        return mm, dd, Rr.grad
+
+    graphed = GraphedMahalAndDet(Rg, Og, xg)
+
+    def loglik_grad_graphed():
+        return graphed(Rg, Og, xg)
+
+    def cpu_loglik_grad():
+        return orc.loglik_grads_autograd(R, O, x)
+
     dec, mm, dd, w = gpu()
     ld_d, mh_d, w_d = dense()
     _, mm_o, dd_o, w_o = cpu()
+    mh_g, ld_g, gR_g, _, _ = loglik_grad_graphed()
+    _, _, gR_e = loglik_grad_eager()
     return {"config": "cfg1: n=1000, l=3, fp64, decompose + mahal_and_det + solve",
             "gpu_ms": gpu_time(gpu, reps), "reference_cpu_ms": cpu_time(cpu), "dense_cholesky_cpu_ms": cpu_time(dense),
+            "loglik_grad_gpu_eager_ms": gpu_time(loglik_grad_eager, reps),
+            "loglik_grad_gpu_cuda_graph_ms": gpu_time(loglik_grad_graphed, reps),
+            "loglik_grad_reference_cpu_ms": cpu_time(cpu_loglik_grad),
+            "graph_vs_eager": {"mahal": rel(mh_g, mm), "logdet": rel(ld_g, dd), "gR": rel(gR_g, gR_e)},
             "cores": torch.get_num_threads(),
             "parity_vs_reference_path": {"mahal": rel(mm, mm_o), "logdet": rel(dd, dd_o), "solve": rel(w, w_o)},
             "parity_vs_dense": {"mahal": rel(mm, mh_d), "logdet": rel(dd, ld_d), "solve": rel(w, w_d)}}
@@ -141,11 +163,19 @@ def cfg3(reps):
             dec = orc.factor(*ref.compute_posterior_precision(ts))
             return orc.solve(dec, ref.compute_v(xs)), orc.selected_inverse(dec)
 
+    from cyclic_gps.graphs import GraphedMahalAndDet
+    with torch.no_grad():
+        model.register_model_matrices_from_params()
+        _, shift_g = model._obs_terms()
+        Kr, Ko = model._precision_blocks(tsg, shift_g)
+        vg = model.compute_v(xsg)
+    graphed = GraphedMahalAndDet(Kr, Ko, vg)
     ll, ll_o = step(), ref_step()
     g_err = max(rel(getattr(model, k).grad, getattr(ref, k).grad) for k in ("N_params", "R_params", "Lambda_params", "B"))
     (mean, cov), (mean_o, (sd, so)) = posterior(), ref_posterior()
     return {"config": "cfg3: CO2-shaped, n=502 (240-unit gap), l=16, fp64, obs_dim=1",
             "gpu_train_step_ms": gpu_time(step, reps), "gpu_posterior_ms": gpu_time(posterior, reps),
+            "gpu_cr_loglik_grad_cuda_graph_ms": gpu_time(lambda: graphed(Kr, Ko, vg), reps),
             "reference_cpu_train_step_ms": cpu_time(ref_step), "reference_cpu_posterior_ms": cpu_time(ref_posterior),
             "cores": torch.get_num_threads(),
             "parity": {"loglik": rel(ll, ll_o), "param_grads": g_err, "posterior_mean": rel(mean, mean_o),
@@ -167,7 +197,7 @@ def kalman_loglik(A, Q, H, Rm, xs):
     return ll
 
 
-def cfg5(reps, max_n):
+def cfg5(reps, max_n, cpu_budget_ms=60e3):
     from cyclic_gps import cyclic_reduction as cr
     from cyclic_gps.synth import leg_precision_blocks
     from oracle import cr_oracle as orc
@@ -182,8 +212,13 @@ def cfg5(reps, max_n):
         B = torch.full((2, l), 0.5 / l ** 0.5, dtype=torch.float64)
         B[1] *= torch.linspace(0.5, 1.5, l, dtype=torch.float64)
         LLT = 0.55 * torch.eye(2, dtype=torch.float64)
+        last_ref = last_kal = None          # (n, posterior ms, loglik ms) / (n, ms) of the largest size actually timed on the CPU
         for n in (10 ** 3, 10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7):
-            if n > max_n or n * l * l * 8 * 14 > 120e9:
+            if n > max_n:
+                continue
+            if n * l * l * 8 * 14 > 150e9:
+                out.append({"l": l, "n": n, "skipped": "does not fit one 180 GB B200 in fp64: blocks %.0f GB + factors %.0f GB + selected inverse %.0f GB"
+                            % (2 * n * l * l * 8 / 1e9, 3 * n * l * l * 8 / 1e9, 2 * n * l * l * 8 / 1e9)})
                 continue
             gaps = torch.ones((1, n - 1), dtype=torch.float64, device=dev)
             R, O = leg_precision_blocks(gaps, G.to(dev), B.to(dev), LLT.to(dev), torch.float64, chunk=max(1 << 14, (1 << 26) // (l * l)))
@@ -200,7 +235,8 @@ def cfg5(reps, max_n):
 
             row = {"l": l, "n": n, "gpu_posterior_ms": gpu_time(posterior, reps), "gpu_loglik_ms": gpu_time(loglik, reps)}
             row["gpu_posterior_rows_per_s"] = n / (row["gpu_posterior_ms"] * 1e-3)
-            if n <= 10 ** 5 and n * l * l <= 10 ** 7:
+            est = None if last_ref is None else last_ref[1] * n / last_ref[0]
+            if est is None or est <= cpu_budget_ms:
                 Rc, Oc, vc = R.cpu(), O.cpu(), v.cpu()
 
                 def ref_posterior():
@@ -209,18 +245,28 @@ def cfg5(reps, max_n):
 
                 row["reference_cpu_posterior_ms"] = cpu_time(ref_posterior, reps=1)
                 row["reference_cpu_loglik_ms"] = cpu_time(lambda: orc.mahal_and_logdet(Rc, Oc, vc), reps=1)
+                last_ref = (n, row["reference_cpu_posterior_ms"], row["reference_cpu_loglik_ms"])
                 (w, (sd, so)), (w_o, (sd_o, so_o)) = posterior(), ref_posterior()
                 mm, dd = loglik()
                 mm_o, dd_o = orc.mahal_and_logdet(Rc, Oc, vc)
                 row["parity"] = {"mean": rel(w, w_o), "cov_diag": rel(sd, sd_o), "cov_off": rel(so, so_o), "mahal": rel(mm, mm_o),
                                  "logdet": rel(dd, dd_o)}
-            if n <= 10 ** 4:
+            elif last_ref is not None:      # the reference scales linearly in n (kalman_timing_script.py:77,85): extrapolated, and marked so
+                row["reference_cpu_posterior_ms_extrapolated"] = last_ref[1] * n / last_ref[0]
+                row["reference_cpu_loglik_ms_extrapolated"] = last_ref[2] * n / last_ref[0]
+                row["reference_cpu_extrapolated_from_n"] = last_ref[0]
+            kest = None if last_kal is None else last_kal[1] * n / last_kal[0]
+            if kest is not None and kest > cpu_budget_ms:
+                row["numpy_kalman_loglik_ms_extrapolated"] = kest
+                row["numpy_kalman_extrapolated_from_n"] = last_kal[0]
+            else:
                 Ad = expm(-0.5 * G.numpy())
                 Qd = np.eye(l) - Ad @ Ad.T
                 xs_c = xs.cpu().numpy()
                 t0 = time.perf_counter()
                 kll = kalman_loglik(Ad, Qd, B.numpy(), LLT.numpy(), xs_c)
                 row["numpy_kalman_loglik_ms"] = (time.perf_counter() - t0) * 1e3
+                last_kal = (n, row["numpy_kalman_loglik_ms"])
                 # LEG log-likelihood from the CR quantities (models.py:301-372) vs the Kalman filter
                 mm, dd = loglik()
                 white = torch.linalg.solve(LLT.to(dev), xs.T).T
@@ -240,6 +286,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--max-n", type=int, default=10 ** 7)
     ap.add_argument("--only", default="1,3,5")
+    ap.add_argument("--cpu-budget-s", type=float, default=60.0, help="cfg5: largest single CPU comparator run that is still timed (larger n: extrapolated)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device")
@@ -250,7 +297,7 @@ def main():
     if "3" in args.only:
         res["cfg3"] = cfg3(args.reps)
     if "5" in args.only:
-        res["cfg5"] = cfg5(max(3, args.reps // 2), args.max_n)
+        res["cfg5"] = cfg5(max(3, args.reps // 2), args.max_n, args.cpu_budget_s * 1e3)
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(res, fh, indent=1)

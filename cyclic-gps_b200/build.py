@@ -98,6 +98,8 @@ def build(force=False, jobs=None, verbose=False, only=None):
                                                               "-c", os.path.join(CSRC, "cr_inst.cu"), "-o", obj]))
     abi_obj = os.path.join(BUILD, "cr_abi.o")
     units.append((abi_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_abi.cu"), "-o", abi_obj]))
+    peg_obj = os.path.join(BUILD, "cr_peg_inst.o")          # precision-block builder (cr_peg.cuh), ell = 1..8, both dtypes
+    units.append((peg_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_peg_inst.cu"), "-o", peg_obj]))
     jobs = jobs or min(len(units), os.cpu_count() or 4)
     # longest units (large ell) first
     units.sort(key=lambda u: -int(u[0].rsplit("_", 1)[-1].split(".")[0]) if "inst_" in u[0] else 0)

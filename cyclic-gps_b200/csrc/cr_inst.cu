@@ -51,8 +51,11 @@ struct CsSel {
 
 template <int L>
 struct Dispatch {
-  // the warp-per-node DMMA family is the automatic choice wherever neither the thread-per-node nor the column-split family exists
+  // The warp-per-node DMMA family exists for ell >= 8.  It is the automatic choice where it measured faster than the
+  // lane-per-row kernels on B200 (profiles/r2_ell_sweep.json): fp64 ell >= 10 and fp32 ell >= 17 (fp32 data has half the bytes for
+  // the same fp64 arithmetic, so the cross-over sits higher).
   static constexpr bool kMma = CRB_HAVE_MMA && (L >= 8);
+  static constexpr bool kMmaAuto = kMma && (sizeof(CRB_T) == 8 ? L >= 10 : L >= 17);
   static constexpr bool kSmallFamilies =
 #if CRB_HAVE_TPN
       TpnFwdCfg<CRB_T, L>::ELIGIBLE || CsSel<L>::FWD;
@@ -63,7 +66,7 @@ struct Dispatch {
     if (ell == L) {
 #if CRB_HAVE_MMA
       if constexpr (kMma) {
-        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies)) return launch_mma_fwd<CRB_T, L>(a, s);
+        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies && kMmaAuto)) return launch_mma_fwd<CRB_T, L>(a, s);
       } else
 #endif
       {
@@ -93,7 +96,7 @@ struct Dispatch {
     if (ell == L) {
 #if CRB_HAVE_MMA
       if constexpr (kMma) {
-        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies)) return launch_mma_bwd<CRB_T, L>(a, s);
+        if (a.variant == CRB200_MMA || (a.variant == CRB200_AUTO && !kSmallFamilies && kMmaAuto)) return launch_mma_bwd<CRB_T, L>(a, s);
       } else
 #endif
       {
@@ -143,7 +146,7 @@ struct Dispatch {
     if (CsSel<L>::FWD) return CsFwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::OWN;
 #endif
 #if CRB_HAVE_MMA
-    if (kMma) return MmaFwdCfg<CRB_T, L>::OWN;
+    if (kMmaAuto) return MmaFwdCfg<CRB_T, L>::OWN;
 #endif
     return FwdCfg<CRB_T, L>::NG - 1;
   }
@@ -154,7 +157,7 @@ struct Dispatch {
     if (CsSel<L>::BWD) return CsBwdCfg<CRB_T, L, (CsSel<L>::LPN > 1 ? CsSel<L>::LPN : 2)>::NT;
 #endif
 #if CRB_HAVE_MMA
-    if (kMma) return MmaBwdCfg<CRB_T, L>::NT;
+    if (kMmaAuto) return MmaBwdCfg<CRB_T, L>::NT;
 #endif
     return BwdCfg<CRB_T, L>::NG;
   }

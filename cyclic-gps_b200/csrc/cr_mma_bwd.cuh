@@ -77,67 +77,56 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
   }
 
   // ---------------- stage in ----------------
-  if (valid) {
-    mma_pad_block<L, LP>(T0, true, lane);
-    mma_stage_block<T, L, LP>(T0, static_cast<const T*>(a.D) + ((size_t)b * E + e) * BS, lane, is_aligned16(a.D));
-  } else {
-    mma_fill_block<LP>(T0, true, lane);
+  // vectors first (plain loads whose latency is covered by the block copies issued next)
+  double x_v = 0.0, wt_v = 0.0, lw_v = 0.0;
+  if (do_w && lane < L) {
+    if (valid) x_v = (double)static_cast<const T*>(a.xk)[((size_t)b * E + e) * L + lane];
+    if (has_odd) wt_v = (double)static_cast<const T*>(a.w_in)[((size_t)b * o + e) * L + lane];
+    if (warp == 0) {
+      if (e0 >= 1) lw_v = (double)static_cast<const T*>(a.w_in)[((size_t)b * o + (e0 - 1)) * L + lane];
+      else if (halo) lw_v = (double)static_cast<const T*>(a.w_halo)[(size_t)b * L + lane];
+    }
   }
-  if (has_odd) {
-    mma_pad_block<L, LP>(T1, false, lane);
-    mma_stage_block<T, L, LP>(T1, static_cast<const T*>(a.F) + ((size_t)b * o + e) * BS, lane, is_aligned16(a.F));
-  } else {
-    mma_fill_block<LP>(T1, false, lane);
-  }
+  const bool st3 = do_sigma && has_odd, st4 = do_sigma && has_so, stl = do_sigma && warp == 0 && (e0 >= 1 || halo);
+  if (valid) mma_stage_issue<T, L, LP>(T0, static_cast<const T*>(a.D) + ((size_t)b * E + e) * BS, true, lane, is_aligned16(a.D));
+  else mma_fill_block<LP>(T0, true, lane);
+  if (has_odd) mma_stage_issue<T, L, LP>(T1, static_cast<const T*>(a.F) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.F));
+  else mma_fill_block<LP>(T1, false, lane);
   if (has_left) {
-    mma_pad_block<L, LP>(T2, false, lane);
-    if (e >= 1) mma_stage_block<T, L, LP>(T2, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e - 1)) * BS, lane, is_aligned16(a.G));
-    else mma_stage_block<T, L, LP>(T2, static_cast<const T*>(a.G_halo) + (size_t)b * BS, lane, is_aligned16(a.G_halo));
+    if (e >= 1) mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e - 1)) * BS, false, lane, is_aligned16(a.G));
+    else mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G_halo) + (size_t)b * BS, false, lane, is_aligned16(a.G_halo));
   } else {
     mma_fill_block<LP>(T2, false, lane);
   }
   if (do_sigma) {
-    if (has_odd) {
-      mma_pad_block<L, LP>(T3, false, lane);
-      mma_stage_block<T, L, LP>(T3, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + e) * BS, lane, is_aligned16(a.Sd_in));
-    } else {
-      mma_fill_block<LP>(T3, false, lane);
-    }
-    if (has_so) {
-      mma_pad_block<L, LP>(T4, false, lane);
-      if (e >= 1) mma_stage_block<T, L, LP>(T4, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e - 1)) * BS, lane, is_aligned16(a.So_in));
-      else mma_stage_block<T, L, LP>(T4, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, lane, is_aligned16(a.So_halo_in));
+    if (st3) mma_stage_issue<T, L, LP>(T3, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.Sd_in));
+    else mma_fill_block<LP>(T3, false, lane);
+    if (st4) {
+      if (e >= 1) mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e - 1)) * BS, false, lane, is_aligned16(a.So_in));
+      else mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, false, lane, is_aligned16(a.So_halo_in));
     } else {
       mma_fill_block<LP>(T4, false, lane);
     }
     if (warp == 0) {
-      double* lsd = base;
-      if (e0 >= 1) {
-        mma_pad_block<L, LP>(lsd, false, lane);
-        mma_stage_block<T, L, LP>(lsd, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1)) * BS, lane, is_aligned16(a.Sd_in));
-      } else if (halo) {
-        mma_pad_block<L, LP>(lsd, false, lane);
-        mma_stage_block<T, L, LP>(lsd, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, lane, is_aligned16(a.Sd_halo));
-      } else {
-        mma_fill_block<LP>(lsd, false, lane);
-      }
+      if (e0 >= 1) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1)) * BS, false, lane, is_aligned16(a.Sd_in));
+      else if (halo) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, false, lane, is_aligned16(a.Sd_halo));
+      else mma_fill_block<LP>(base, false, lane);
     }
   }
   if (lane < LP) {
-    const bool in = lane < L;
-    X[lane] = (do_w && valid && in) ? (double)static_cast<const T*>(a.xk)[((size_t)b * E + e) * L + lane] : 0.0;
-    WT[lane] = (do_w && has_odd && in) ? (double)static_cast<const T*>(a.w_in)[((size_t)b * o + e) * L + lane] : 0.0;
+    X[lane] = x_v;
+    WT[lane] = wt_v;
     WV[lane] = 0.0;
-    if (warp == 0) {
-      double v = 0.0;
-      if (do_w && in) {
-        if (e0 >= 1) v = (double)static_cast<const T*>(a.w_in)[((size_t)b * o + (e0 - 1)) * L + lane];
-        else if (halo) v = (double)static_cast<const T*>(a.w_halo)[(size_t)b * L + lane];
-      }
-      base[BLK + lane] = v;
-    }
+    if (warp == 0) base[BLK + lane] = lw_v;
   }
   cp_async_wait_all();
+  __syncwarp();
+  if (valid) mma_stage_finish<T, L, LP>(T0, true, lane);
+  if (has_odd) mma_stage_finish<T, L, LP>(T1, false, lane);
+  if (has_left) mma_stage_finish<T, L, LP>(T2, false, lane);
+  if (st3) mma_stage_finish<T, L, LP>(T3, false, lane);
+  if (st4) mma_stage_finish<T, L, LP>(T4, false, lane);
+  if (stl) mma_stage_finish<T, L, LP>(base, false, lane);
   __syncthreads();                                      // the left neighbour's S~_d and w~ are visible
 
   // ---------------- Di, P, Q, w ----------------

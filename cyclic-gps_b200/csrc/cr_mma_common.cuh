@@ -1,5 +1,5 @@
 // Warp-per-node building blocks of the large-block kernel family (cr_mma_fwd.cuh / cr_mma_bwd.cuh):
-// fp32 ell >= 11 and fp64 ell >= 9, where a block no longer fits one thread's registers.
+// blocks that no longer fit one thread's registers (automatic for fp64 ell >= 10 and fp32 ell >= 17, see cr_inst.cu).
 //
 // One WARP owns one even node.  Every ell x ell block lives in shared memory as a padded
 // LP x LD row-major matrix of DOUBLES (LP = ell rounded up to a multiple of 8, LD = LP + 4), whatever the
@@ -108,7 +108,9 @@ __device__ __forceinline__ void acc_mirror_from_smem(double (&acc)[LP / 8][LP / 
 // one pair (row, col), (row, col + 1) of a block -> global storage type T, dense ell x ell rows
 template <typename T, int L>
 __device__ __forceinline__ void frag_pair_store(T* __restrict__ g, const int row, const int col, const double v0, const double v1, const bool vec_ok) {
-  if (row >= L || col >= L) return;
+  if constexpr (L % 8 != 0) {           // padded block: rows / columns >= L do not exist in global memory
+    if (row >= L || col >= L) return;
+  }
   T* p = g + row * L + col;
   if constexpr ((L % 2) == 0) {
     if (vec_ok) {
@@ -165,6 +167,17 @@ __device__ __forceinline__ void mma_stage_block(double* S, const T* __restrict__
     if constexpr ((L % 2) == 0) {
       if (vec_ok) {
         constexpr int CPR = L / 2, TOT = L * CPR;
+        if constexpr ((32 % CPR) == 0 && (TOT % 32) == 0) {
+          // a warp step of 32 chunks covers 32 / CPR whole rows: both addresses are plain induction variables
+          const int r0 = lane / CPR, c0 = lane - r0 * CPR;
+          unsigned sa = smem_u32(S + r0 * LD + 2 * c0);
+          const char* gp = reinterpret_cast<const char*>(g) + (size_t)lane * 16;
+          constexpr unsigned sstep = (32 / CPR) * LD * 8;
+#pragma unroll
+          for (int i = 0; i < TOT / 32; ++i, sa += sstep, gp += 512)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gp) : "memory");
+          return;
+        }
         for (int i = lane; i < TOT; i += 32) {
           const int r = i / CPR, c = i - r * CPR;
           cp_async16(S + r * LD + 2 * c, g + r * L + 2 * c);
@@ -199,6 +212,70 @@ __device__ __forceinline__ void mma_stage_block(double* S, const T* __restrict__
   }
 }
 
+// fp32 storage, asynchronous: cp.async the raw ell x ell floats into the TAIL of the block's own shared memory
+// (mma_stage_raw_f32), and after the copy has landed widen them in place (mma_widen_f32: every lane first reads all its
+// elements into registers, then the warp writes the padded doubles -- the two regions overlap).
+template <int L, int LP>
+__device__ __forceinline__ float* mma_raw_f32(double* S) {
+  constexpr int RAWF = (L * L + 3) / 4 * 4;
+  return reinterpret_cast<float*>(S + LP * (LP + 4)) - RAWF;
+}
+template <int L, int LP>
+__device__ __forceinline__ void mma_stage_raw_f32(double* S, const float* __restrict__ g, const int lane, const bool vec_ok) {
+  float* raw = mma_raw_f32<L, LP>(S);
+  if constexpr ((L * L) % 4 == 0) {
+    if (vec_ok) {
+      for (int i = lane; i < L * L / 4; i += 32) cp_async16(raw + 4 * i, g + 4 * i);
+      return;
+    }
+  }
+  for (int i = lane; i < L * L; i += 32) cp_async4(raw + i, g + i);
+}
+template <int L, int LP>
+__device__ __forceinline__ void mma_widen_f32(double* S, const bool identity, const int lane) {
+  constexpr int LD = LP + 4, PER = (L * L + 31) / 32;
+  const float* raw = mma_raw_f32<L, LP>(S);
+  float v[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < L * L ? raw[i] : 0.f;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    if (i < L * L) {
+      const int r = i / L, c = i - r * L;
+      S[r * LD + c] = (double)v[k];
+    }
+  }
+  mma_pad_block<L, LP>(S, identity, lane);
+}
+
+// one call per block for either storage type: issue the copy now ...
+template <typename T, int L, int LP>
+__device__ __forceinline__ void mma_stage_issue(double* S, const T* __restrict__ g, const bool identity, const int lane, const bool vec_ok) {
+  if constexpr (sizeof(T) == 8) {
+    mma_pad_block<L, LP>(S, identity, lane);
+    mma_stage_block<T, L, LP>(S, g, lane, vec_ok);
+  } else {
+    mma_stage_raw_f32<L, LP>(S, g, lane, vec_ok);
+  }
+}
+// ... and finish it after cp_async_wait_all + __syncwarp (fp32: widen in place; fp64: nothing left to do)
+template <typename T, int L, int LP>
+__device__ __forceinline__ void mma_stage_finish(double* S, const bool identity, const int lane) {
+  if constexpr (sizeof(T) == 4) mma_widen_f32<L, LP>(S, identity, lane);
+}
+
+// CTA-internal producer / consumer hand-over between two warps on a named barrier (ids 1..15)
+__device__ __forceinline__ void pair_arrive(const int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 64;\n" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void pair_wait(const int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
 template <typename T, int L>
 __device__ __forceinline__ void mma_stage_vec(double* S, const T* __restrict__ g, const int lane) {
   for (int i = lane; i < L; i += 32) S[i] = (double)g[i];
@@ -211,6 +288,18 @@ __device__ __forceinline__ void mma_store_block_f(T* __restrict__ g, const doubl
   if constexpr (sizeof(T) == 8 && (L % 2) == 0) {
     if (vec_ok) {
       constexpr int CPR = L / 2, TOT = L * CPR;
+      if constexpr ((32 % CPR) == 0 && (TOT % 32) == 0) {
+        const int r0 = lane / CPR, c0 = 2 * (lane - r0 * CPR);
+        const double* sp = S + r0 * LD + c0;
+        double2* gp = reinterpret_cast<double2*>(g) + lane;
+#pragma unroll
+        for (int i = 0; i < TOT / 32; ++i, sp += (32 / CPR) * LD, gp += 32) {
+          const double2 v = *reinterpret_cast<const double2*>(sp);
+          const int r = r0 + i * (32 / CPR);
+          *gp = make_double2(f(r, c0, v.x), f(r, c0 + 1, v.y));
+        }
+        return;
+      }
       for (int i = lane; i < TOT; i += 32) {
         const int r = i / CPR, c = 2 * (i - r * CPR);
         const double2 v = *reinterpret_cast<const double2*>(S + r * LD + c);
@@ -246,65 +335,79 @@ __device__ __forceinline__ void mma_store_block(T* __restrict__ g, const double*
 // ---------------------------------------------------------------------------------------------------------
 // serial parts, one warp, lane = row (Cholesky) / lane = column (inverse)
 // ---------------------------------------------------------------------------------------------------------
-// In-place Cholesky of the SPD block in S (lower triangle read; exact zeros written above the diagonal).
+// In-place Cholesky of the SPD block in S (lower triangle read; exact zeros written above the diagonal), right-looking:
+// lane r keeps row r in registers; once column j is final it is published through a small double-buffered vector
+// (`colbuf`, 2 * LP doubles) and every lane applies the rank-1 update to the rest of its row -- LP - j independent
+// FMAs, so the serial chain per column is only pivot broadcast -> rsqrt -> scale -> publish.
 // invd[j] = 1 / K[j][j] on every lane.  Returns true when a pivot was not positive.
 template <int LP>
-__device__ __forceinline__ bool warp_cholesky(double* S, double (&invd)[LP], const int lane) {
+__device__ __forceinline__ bool warp_cholesky(double* S, double* colbuf, double (&invd)[LP], const int lane) {
   constexpr int LD = LP + 4;
   const bool act = lane < LP;
   const int r = act ? lane : LP - 1;        // idle lanes shadow the last row and never store
-  double Lr[LP];
+  double a[LP];
 #pragma unroll
   for (int c = 0; c < LP; c += 2) {
     const double2 v = *reinterpret_cast<const double2*>(S + r * LD + c);
-    Lr[c] = v.x; Lr[c + 1] = v.y;
+    a[c] = v.x; a[c + 1] = v.y;
   }
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < LP; ++j) {
-    // left-looking: s = A[r][j] - sum_{k<j} L[r][k] L[j][k]; row j of L is complete in shared memory (broadcast reads)
-    double s0 = Lr[j], s1 = 0.0;
-#pragma unroll
-    for (int k = 0; k + 1 < j; k += 2) {
-      const double2 lj = *reinterpret_cast<const double2*>(S + j * LD + k);
-      s0 = fma(-Lr[k], lj.x, s0);
-      s1 = fma(-Lr[k + 1], lj.y, s1);
-    }
-    if (j & 1) s0 = fma(-Lr[j - 1], S[j * LD + j - 1], s0);
-    const double s = s0 + s1;
-    const double d = __shfl_sync(0xffffffffu, s, j);
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
     if (!(d > 0.0)) bad = true;
     const double inv = rsqrt(d);
     invd[j] = inv;
-    Lr[j] = (r > j) ? s * inv : (r == j ? d * inv : 0.0);
-    if (act) S[r * LD + j] = Lr[j];
+    const double l = (r > j) ? a[j] * inv : (r == j ? d * inv : 0.0);
+    a[j] = l;
+    double* cb = colbuf + (j & 1) * LP;
+    if (act) cb[r] = l;
     __syncwarp();
+    // a[c] -= L[r][j] L[c][j] for c > j (entries with c > r are never used)
+    if (((j + 1) & 1) != 0 && j + 1 < LP) a[j + 1] = fma(-l, cb[j + 1], a[j + 1]);
+#pragma unroll
+    for (int c = (j + 2) & ~1; c < LP; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(cb + c);
+      a[c] = fma(-l, t.x, a[c]);
+      a[c + 1] = fma(-l, t.y, a[c + 1]);
+    }
   }
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < LP; c += 2)
+      *reinterpret_cast<double2*>(S + r * LD + c) = make_double2(c <= r ? a[c] : 0.0, c + 1 <= r ? a[c + 1] : 0.0);
+  }
+  __syncwarp();
   return bad;
 }
 
-// S <- S^{-1} for lower-triangular S with 1 / diag in invd; lane c builds column c by forward substitution
+// S <- S^{-1} for lower-triangular S with 1 / diag in invd.  Lane r builds ROW r of the inverse by a column sweep from
+// the right (y^T K = e_r^T): y_c = acc_c / K_cc, then acc_c' -= y_c K[c][c'] for c' < c -- the updates of one step are
+// independent of each other and read row c of K as a broadcast, so the serial chain per step is one multiply + one FMA.
 template <int LP>
 __device__ __forceinline__ void warp_tri_inverse(double* S, const double (&invd)[LP], const int lane) {
   constexpr int LD = LP + 4;
-  const int c = lane;
-  double z[LP];
+  const bool act = lane < LP;
+  const int r = act ? lane : LP - 1;
+  double acc[LP];
 #pragma unroll
-  for (int r = 0; r < LP; ++r) {
-    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
+  for (int c = 0; c < LP; ++c) acc[c] = (c == r) ? 1.0 : 0.0;
 #pragma unroll
-    for (int k = 0; k + 1 < r; k += 2) {
-      const double2 kr = *reinterpret_cast<const double2*>(S + r * LD + k);
-      s0 = fma(-kr.x, z[k], s0);
-      s1 = fma(-kr.y, z[k + 1], s1);
+  for (int c = LP - 1; c >= 0; --c) {
+    const double y = acc[c] * invd[c];      // Ki[r][c] (exactly zero for c > r)
+    acc[c] = y;
+#pragma unroll
+    for (int k = 0; k + 1 < c; k += 2) {
+      const double2 kc = *reinterpret_cast<const double2*>(S + c * LD + k);
+      acc[k] = fma(-y, kc.x, acc[k]);
+      acc[k + 1] = fma(-y, kc.y, acc[k + 1]);
     }
-    if (r & 1) s0 = fma(-S[r * LD + r - 1], z[r - 1], s0);
-    z[r] = (r >= c) ? (s0 + s1) * invd[r] : 0.0;
+    if (c & 1) acc[c - 1] = fma(-y, S[c * LD + c - 1], acc[c - 1]);
   }
   __syncwarp();        // every lane is done reading the factor
-  if (c < LP) {
+  if (act) {
 #pragma unroll
-    for (int r = 0; r < LP; ++r) S[r * LD + c] = z[r];
+    for (int c = 0; c < LP; c += 2) *reinterpret_cast<double2*>(S + r * LD + c) = make_double2(acc[c], acc[c + 1]);
   }
   __syncwarp();
 }

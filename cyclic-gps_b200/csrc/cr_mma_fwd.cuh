@@ -2,7 +2,7 @@
 //
 // Same contract as cr_level_fwd_kernel (see cr_level_fwd.cuh for the maths and the reference lines it replaces:
 // cyclic_gps/cyclic_reduction.py:204-259, :412-427).  Used where a block no longer fits one thread's registers
-// (fp32 ell >= 11, fp64 ell >= 9).  The triangular solves of the reference are restated as products with the explicit
+// (automatic for fp64 ell >= 10, fp32 ell >= 17).  The triangular solves of the reference are restated as products with the explicit
 // inverse Ki = K^{-1} (formed once per node by forward substitution), so that everything of order ell^3 is a dense
 // product on mma.sync.m8n8k4.f64:
 //   K  = chol(R_{2e})                    warp_cholesky (lane = row)            -> D output
@@ -14,7 +14,8 @@
 //   R~_e = R_{2e+1} - A_e - B_{e+1} ;  y~_e = y_{2e+1} - F x_e - G_e x_{e+1}
 // A CTA is W warps = W consecutive even nodes of one series: W - 1 owned nodes plus the next even node as a
 // read-only halo (its B and G x are needed by the last owned node; it skips everything else).  The only exchange
-// between warps is B / G x of the right neighbour through shared memory, behind ONE __syncthreads.
+// between warps is B / G x of the right neighbour through shared memory, handed over on a named barrier per pair of
+// neighbouring warps (no CTA-wide barrier: the warps of a CTA drift apart and cover each other's serial phases).
 // Per node shared memory holds four padded blocks of doubles, each used several times:
 //   S0: R_even -> K -> Ki      S2: O_right -> F      S3: O_left -> G -> B      S4: R_odd
 // O~ and R~ leave straight from the accumulator fragments; K, F, G leave from shared memory as coalesced rows.
@@ -29,7 +30,7 @@ struct MmaFwdCfg {
   using Geo = MmaGeom<L>;
   static constexpr bool ELIGIBLE = (L >= 8);
   static constexpr int LP = Geo::LP, LD = Geo::LD, BLK = Geo::BLK;
-  static constexpr int VEC = 4 * LP;                          // y_even -> x | y_odd | G x | spare
+  static constexpr int VEC = 6 * LP;                          // y_even -> x | y_odd | G x | spare | column buffer (2 LP) of the Cholesky
   static constexpr int REC = 4 * BLK + VEC;                   // doubles per node
   static constexpr int W = LP <= 16 ? 8 : (LP <= 24 ? 5 : 6); // warps (= nodes incl. the halo) per CTA
   static constexpr int OWN = W - 1;
@@ -74,38 +75,42 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   const bool vR = is_aligned16(gR), vO = is_aligned16(gO);
 
   // ---------------- stage in ----------------
-  if (valid) {
-    mma_pad_block<L, LP>(S0, true, lane);
-    mma_stage_block<T, L, LP>(S0, gR + (size_t)(2 * e) * BS, lane, vR);
-  } else {
-    mma_fill_block<LP>(S0, true, lane);
+  // vectors first (plain loads whose latency is covered by the block copies issued next)
+  double ye_v = 0.0, yo_v = 0.0;
+  if (has_y && lane < L) {
+    if (valid) ye_v = (double)gy[(size_t)(2 * e) * L + lane];
+    if (do_f) yo_v = (double)gy[(size_t)(2 * e + 1) * L + lane];
   }
-  if (has_left) {
-    mma_pad_block<L, LP>(S3, false, lane);
-    if (e >= 1) mma_stage_block<T, L, LP>(S3, gO + (size_t)(2 * e - 1) * BS, lane, vO);
-    else mma_stage_block<T, L, LP>(S3, static_cast<const T*>(a.O_halo) + (size_t)b * BS, lane, is_aligned16(a.O_halo));
-  } else {
-    mma_fill_block<LP>(S3, false, lane);
-  }
+  const T* srcL = has_left ? (e >= 1 ? gO + (size_t)(2 * e - 1) * BS : static_cast<const T*>(a.O_halo) + (size_t)b * BS) : nullptr;
+  const bool vL = e >= 1 ? vO : is_aligned16(a.O_halo);
+  if (valid) mma_stage_issue<T, L, LP>(S0, gR + (size_t)(2 * e) * BS, true, lane, vR);
+  else mma_fill_block<LP>(S0, true, lane);
+  if (has_left) mma_stage_issue<T, L, LP>(S3, srcL, false, lane, vL);
+  else mma_fill_block<LP>(S3, false, lane);
   if (do_f) {
-    mma_pad_block<L, LP>(S2, false, lane);
-    mma_pad_block<L, LP>(S4, false, lane);
-    mma_stage_block<T, L, LP>(S2, gO + (size_t)(2 * e) * BS, lane, vO);
-    mma_stage_block<T, L, LP>(S4, gR + (size_t)(2 * e + 1) * BS, lane, vR);
+    mma_stage_issue<T, L, LP>(S2, gO + (size_t)(2 * e) * BS, false, lane, vO);
+    mma_stage_issue<T, L, LP>(S4, gR + (size_t)(2 * e + 1) * BS, false, lane, vR);
   }
   if (lane < LP) {
-    YE[lane] = (has_y && valid && lane < L) ? (double)gy[(size_t)(2 * e) * L + lane] : 0.0;
-    YO[lane] = (has_y && do_f && lane < L) ? (double)gy[(size_t)(2 * e + 1) * L + lane] : 0.0;
+    YE[lane] = ye_v;
+    YO[lane] = yo_v;
     V[lane] = 0.0;
   }
   cp_async_wait_all();
+  __syncwarp();
+  if (valid) mma_stage_finish<T, L, LP>(S0, true, lane);
+  if (has_left) mma_stage_finish<T, L, LP>(S3, false, lane);
+  if (do_f) {
+    mma_stage_finish<T, L, LP>(S2, false, lane);
+    mma_stage_finish<T, L, LP>(S4, false, lane);
+  }
   __syncwarp();
 
   // ---------------- K, Ki, x ----------------
   double ld_part = 0.0, mh_part = 0.0;
   {
     double invd[LP];
-    const bool bad = warp_cholesky<LP>(S0, invd, lane);
+    const bool bad = warp_cholesky<LP>(S0, N + 4 * BLK + 4 * LP, invd, lane);
     if (own) {
       if (bad && a.info != nullptr && lane == 0) {
         const long long flat = (long long)b * E + e;
@@ -194,14 +199,15 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
       }
     } else {
       __syncwarp();                                   // G has left for global memory and is not needed any more
-      acc_to_smem<LP>(S3, acc, 1.0, lane);            // B over G, read by the warp to the left after the barrier
+      acc_to_smem<LP>(S3, acc, 1.0, lane);            // B over G, read by the warp to the left after the hand-over
     }
   }
+  if (warp > 0) pair_arrive(warp);                    // B and G x of this node are in shared memory (barrier id = consumer warp + 1)
   if (do_f) {
     acc_zero<LP>(acc);
     warp_gemm<LP, false, true, K_FULL, false>(acc, S2, S2, lane);          // A = F F^T, kept in registers
   }
-  __syncthreads();                                    // B and G x of the right neighbour are visible
+  if (warp < OWN) pair_wait(warp + 1);                // B and G x of the right neighbour are visible
 
   // ---------------- R~_e = R_odd - A - B_{e+1},  y~_e = y_odd - F x_e - G_e x_{e+1} ----------------
   if (do_f && a.Rn != nullptr) {

@@ -79,7 +79,25 @@ class SweepHsArgs(C.Structure):
                 ("X", _vp), ("scry", _vp * 2), ("mahal", _vp)]
 
 
-EXPORTS = ("crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
+_dp = C.POINTER(C.c_double)
+
+
+class PegFwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
+                ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp), ("shift", _vp),
+                ("R", _vp), ("O", _vp), ("strideR", _ll), ("strideO", _ll), ("info", _vp), ("nterms", _i)]
+
+
+class PegBwdArgs(C.Structure):
+    _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
+                ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp),
+                ("V_re", _vp), ("V_im", _vp), ("Vinv_re", _vp), ("Vinv_im", _vp),
+                ("invdl_re", _vp), ("invdl_im", _vp), ("degenerate", _vp),
+                ("O", _vp), ("strideO", _ll), ("gR", _vp), ("gO", _vp), ("stride_gR", _ll), ("stride_gO", _ll), ("Z", _vp),
+                ("nterms", _i), ("lamfull_re", _vp), ("lamfull_im", _vp)]
+
+
+EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
            "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd", "crb200_sweep_halfsolve",
            "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_launch_count")
 
@@ -121,6 +139,12 @@ def load():
         lib.crb200_sweep_bwd.argtypes = [_i, _i, C.POINTER(SweepBwdArgs), _vp]
         lib.crb200_launch_count.restype = C.c_longlong
         lib.crb200_launch_count.argtypes = []
+        lib.crb200_peg_precision_fwd.restype = _i
+        lib.crb200_peg_precision_fwd.argtypes = [_i, _i, C.POINTER(PegFwdArgs), _vp]
+        lib.crb200_peg_precision_bwd.restype = _i
+        lib.crb200_peg_precision_bwd.argtypes = [_i, _i, C.POINTER(PegBwdArgs), _vp]
+        lib.crb200_peg_max_ell.restype = _i
+        lib.crb200_peg_max_ell.argtypes = []
         for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
             getattr(lib, name).restype = _i
             getattr(lib, name).argtypes = [_i, _i]
@@ -223,6 +247,21 @@ def sweep_bwd(dtype: torch.dtype, ell: int, **fields):
 def sweep_halfsolve(dtype: torch.dtype, ell: int, **fields):
     a = _fill(SweepHsArgs(), fields)
     _check(load().crb200_sweep_halfsolve(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_sweep_halfsolve")
+
+
+def peg_fwd(dtype: torch.dtype, ell: int, **fields):
+    """Precision blocks (R, O) of the LEG process from time gaps (crb200_peg_precision_fwd)."""
+    a = _fill(PegFwdArgs(), fields)
+    _check(load().crb200_peg_precision_fwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_peg_precision_fwd")
+
+
+def peg_bwd(dtype: torch.dtype, ell: int, **fields):
+    a = _fill(PegBwdArgs(), fields)
+    _check(load().crb200_peg_precision_bwd(dtype_code(dtype), ell, C.byref(a), _stream()), "crb200_peg_precision_bwd")
+
+
+def peg_max_ell() -> int:
+    return int(load().crb200_peg_max_ell())
 
 
 def launch_count() -> int:

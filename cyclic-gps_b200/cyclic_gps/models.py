@@ -14,6 +14,7 @@ from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_and_det, solve
 from cyclic_gps.model_utils import build_2x2_block, build_3x3_block, compute_eG, gaussian_stitch
+from cyclic_gps.peg import peg_precision
 
 try:  # pragma: no cover - not installed in the build image
     import pytorch_lightning as pl
@@ -106,19 +107,28 @@ class LEGFamily(_Base):
         self.calc_G()
 
     # ---- precision blocks (reference models.py:181-239, 254-280)
+    @staticmethod
+    def _compute_device(t):
+        """Where the per-row work runs: the current CUDA device when there is one (inputs may live on the CPU, as in the
+        reference's tests; only ts / xs cross PCIe), else the tensor's own device (model glue only -- the CR calls raise)."""
+        if t.is_cuda or not torch.cuda.is_available():
+            return t.device
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _precision_blocks(self, ts, shift=None):
+        """(Rs, Os) on the compute device, built by ONE kernel from the time gaps (cyclic_gps.peg) with a
+        hand-written backward to G and the diagonal shift.  ts (n,) or (B,n)."""
+        dev = self._compute_device(ts)
+        t = ts.to(dev)
+        gaps = (t[..., 1:] - t[..., :-1]).to(self.G.dtype)
+        return peg_precision(gaps, self.G, shift)
+
     def compute_PEG_precision(self, ts):
-        """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision; a leading batch axis of
-        independent series, ts (B,n), gives (B,n,l,l) and (B,n-1,l,l) (the reference is batch-of-one)."""
-        gaps = ts[..., 1:] - ts[..., :-1]
-        eye = torch.eye(self.rank, dtype=self.G.dtype, device=self.G.device)
-        A = torch.matrix_exp(-0.5 * self.G * gaps.unsqueeze(-1).unsqueeze(-1))
-        At = A.transpose(-1, -2)
-        fwd = torch.linalg.solve(eye - A @ At, A)            # (I - A A^T)^{-1} A
-        bwd = torch.linalg.solve(eye - At @ A, At)           # (I - A^T A)^{-1} A^T
-        from_prev, to_next = A @ bwd, At @ fwd
-        diag = torch.cat([(eye + to_next[..., :1, :, :]), eye + from_prev[..., :-1, :, :] + to_next[..., 1:, :, :],
-                          (eye + from_prev[..., -1:, :, :])], dim=-3)
-        return diag, -fwd
+        """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision, on the caller's device; a leading
+        batch axis of independent series, ts (B,n), gives (B,n,l,l) and (B,n-1,l,l) (the reference is batch-of-one,
+        SURVEY 8(f2))."""
+        Rs, Os = self._precision_blocks(ts)
+        return Rs.to(ts.device), Os.to(ts.device)
 
     def _obs_terms(self):
         LLT = self.calc_Lambda_Lambda_T(self.Lambda)
@@ -126,38 +136,46 @@ class LEGFamily(_Base):
 
     def compute_posterior_precision(self, ts):
         _, shift = self._obs_terms()
-        Rs, Os = self.compute_PEG_precision(ts)
-        return Rs + shift, Os
+        Rs, Os = self._precision_blocks(ts, shift)
+        return Rs.to(ts.device), Os.to(ts.device)
 
     def compute_v(self, xs):
+        """v = B^T (LL^T)^{-1} x for every row (reference models.py:270-280): the (d x l) map is formed once on the
+        parameters' device, the per-row work is one matmul on the device of xs."""
         LLT = self.calc_Lambda_Lambda_T(self.Lambda)
-        return torch.linalg.solve(LLT, xs.transpose(-1, -2)).transpose(-1, -2) @ self.B
+        return xs @ torch.linalg.solve(LLT, self.B).to(xs.device)
 
     def compute_insample_posterior(self, ts, xs):
         """Posterior mean (n,l) and {"Rs","Os"} blocks of the posterior covariance
-        (reference models.py:282-298)."""
+        (reference models.py:282-298); computed on the GPU, returned on the caller's device."""
+        dev = self._compute_device(ts)
+        _, shift = self._obs_terms()
         K = {}
-        K["Rs"], K["Os"] = self.compute_posterior_precision(ts)
+        K["Rs"], K["Os"] = self._precision_blocks(ts, shift)
         dec = decompose(**K)
-        mean = solve(dec, self.compute_v(xs))
+        mean = solve(dec, self.compute_v(xs.to(dev)))
         cov = {}
         cov["Rs"], cov["Os"] = inverse_blocks(dec)
-        return mean, cov
+        out = ts.device
+        return mean.to(out), {k: v.to(out) for k, v in cov.items()}
 
     def log_likelihood(self, ts, xs):
         """log p(xs | ts) through two CR factorisations (reference models.py:301-372).  ts (n,), xs (n,d) give a
         scalar as in the reference; a batch of independent series, ts (B,n) and xs (B,n,d), gives (B,) values from
-        ONE batched pass of the CR engine (the series share the model parameters)."""
+        ONE batched pass of the CR engine (the series share the model parameters).  Only ts and xs travel to the GPU:
+        the precision blocks are built there (``_precision_blocks``)."""
         self.register_model_matrices_from_params()
+        dev = self._compute_device(ts)
         LLT, shift = self._obs_terms()
-        white = torch.linalg.solve(LLT, xs.transpose(-1, -2)).transpose(-1, -2)
-        obs_mahal = torch.sum(white * xs, dim=(-1, -2))
-        obs_logdet = torch.logdet(2 * math.pi * LLT) * xs.shape[-2]
-        v = white @ self.B
-        Rs, Os = self.compute_PEG_precision(ts)
+        xs_d = xs.to(dev)
+        white = xs_d @ torch.linalg.inv(LLT).to(dev)          # x^T (LL^T)^{-1} per row (LL^T is d x d and symmetric)
+        obs_mahal = torch.sum(white * xs_d, dim=(-1, -2))
+        obs_logdet = (torch.logdet(2 * math.pi * LLT) * xs.shape[-2]).to(dev)
+        v = white @ self.B.to(dev)
+        Rs, Os = self._precision_blocks(ts)
         prior_logdet = det(decompose(Rs, Os))
-        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift, Os=Os, x=v)
-        return -0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))
+        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift.to(dev), Os=Os, x=v)
+        return (-0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))).to(ts.device)
 
     # ---- predictions at new times (reference models.py:394-546), vectorised over the targets
     def forecast(self, eG, ip_mean, ip_cov):

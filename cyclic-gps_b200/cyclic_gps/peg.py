@@ -1,0 +1,138 @@
+"""Precision blocks of the LEG / PEG process on the device: the step in front of the CR hot path.
+
+``peg_precision(gaps, G, shift)`` replaces ``LEGFamily.compute_PEG_precision`` / ``compute_posterior_precision`` of the
+reference (cyclic_gps/models.py:181-239, 254-268): it turns the time gaps of a batch of series into the diagonal and
+off-diagonal blocks ``(Rs, Os)`` with ONE kernel launch (``crb200_peg_precision_fwd``), and carries a hand-written
+backward (``crb200_peg_precision_bwd``) to ``G`` and ``shift`` -- the per-gap chain through the two linear solves and
+the adjoint of the matrix exponential run on the device, the host only finishes an (l x l) product.  The blocks are
+written once, in the layout the level-0 CR kernel reads; with ``ts`` as the only per-row input a likelihood evaluation
+ships 4 bytes per row to the GPU instead of (2 l^2 + l) elements.
+
+G is eigendecomposed once per call on the host (l x l, as the reference's ``compute_eG`` does, model_utils.py:12-29).
+Block sizes above ``crb200_peg_max_ell()`` (8), an ill-conditioned eigenbasis or CPU-only use fall back to the same
+formulas in torch ops (``peg_precision_torch``), which is also the oracle of the tests."""
+import torch
+
+from . import _engine, _native
+
+EIG_COND_MAX = 1e7      # beyond this the eigen-form of exp(-d/2 G) loses too many digits: use torch.matrix_exp
+
+
+def peg_precision_torch(gaps, G, shift=None):
+    """Reference formulas in torch ops (differentiable by autograd): gaps (..., n-1) -> Rs (..., n, l, l), Os (..., n-1, l, l)."""
+    eye = torch.eye(G.shape[0], dtype=G.dtype, device=G.device)
+    A = torch.matrix_exp(-0.5 * G * gaps.to(G.dtype).unsqueeze(-1).unsqueeze(-1))
+    At = A.transpose(-1, -2)
+    fwd = torch.linalg.solve(eye - A @ At, A)            # (I - A A^T)^{-1} A
+    bwd = torch.linalg.solve(eye - At @ A, At)           # (I - A^T A)^{-1} A^T
+    from_prev, to_next = A @ bwd, At @ fwd
+    base = eye if shift is None else eye + shift
+    if gaps.shape[-1] == 0:
+        return base.expand(gaps.shape[:-1] + (1,) + tuple(base.shape)).clone(), -fwd
+    diag = torch.cat([base + to_next[..., :1, :, :], base + from_prev[..., :-1, :, :] + to_next[..., 1:, :, :],
+                      base + from_prev[..., -1:, :, :]], dim=-3)
+    return diag, -fwd
+
+
+class _EigConsts:
+    """Everything the kernels need about G, as ONE device array of doubles (+ complex V, V^{-1} on the device)."""
+
+    def __init__(self, G, dev):
+        l = G.shape[0]
+        Gc = G.detach().to(torch.float64).cpu()
+        lam, V = torch.linalg.eig(Gc)
+        Vinv = torch.linalg.inv(V)
+        self.cond = float(torch.linalg.cond(V))
+        M = torch.einsum("rk,kc->krc", V, Vinv).reshape(l, l * l)
+        # the expansion exp(cG) - I = Re sum_k (e^{c lam_k} - 1) M_k only needs one member of every conjugate pair (doubled);
+        # real eigenvalues count once.  Terms are packed to the front, the rest is padding that is never read.
+        tol = 1e-12 * float(lam.abs().max().clamp_min(1e-300))
+        keep = [k for k in range(l) if lam[k].imag > tol] + [k for k in range(l) if abs(float(lam[k].imag)) <= tol]
+        n_neg = sum(1 for k in range(l) if lam[k].imag < -tol)
+        if n_neg == sum(1 for k in range(l) if lam[k].imag > tol):
+            w = torch.tensor([2.0 if lam[k].imag > tol else 1.0 for k in keep], dtype=torch.float64)
+            lam_t = torch.cat([lam[keep], torch.zeros(l - len(keep), dtype=lam.dtype)])
+            M_t = torch.cat([M[keep] * w.unsqueeze(1), torch.zeros((l - len(keep), l * l), dtype=M.dtype)])
+            self.nterms = len(keep)
+        else:                                           # (not a conjugate-closed spectrum: cannot happen for real G; keep everything)
+            lam_t, M_t, self.nterms = lam, M, l
+        dl = lam.unsqueeze(1) - lam.unsqueeze(0)
+        deg = dl.abs() <= 1e-9 * lam.abs().max().clamp_min(1e-300)
+        invdl = torch.where(deg, torch.zeros_like(dl), 1.0 / torch.where(deg, torch.ones_like(dl), dl))
+        parts = [lam_t.real, lam_t.imag, M_t.real, M_t.imag, V.real, V.imag, Vinv.real, Vinv.imag, invdl.real, invdl.imag, deg.to(torch.float64),
+                 lam.real, lam.imag]
+        flat = torch.cat([p.reshape(-1).to(torch.float64) for p in parts]).contiguous()
+        self.buf = flat.to(dev)
+        self.V, self.Vinv = V.to(dev), Vinv.to(dev)
+        base, off, ptrs = self.buf.data_ptr(), 0, []
+        for p in parts:
+            ptrs.append(base + 8 * off)
+            off += p.numel()
+        (self.lam_re, self.lam_im, self.M_re, self.M_im, self.V_re, self.V_im, self.Vinv_re, self.Vinv_im,
+         self.invdl_re, self.invdl_im, self.deg, self.lamfull_re, self.lamfull_im) = ptrs
+
+
+class _PegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gaps, G, shift, consts):
+        B, nm1 = gaps.shape
+        n, l, dtype, dev = nm1 + 1, G.shape[0], gaps.dtype, gaps.device
+        R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
+        O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        sh = shift.detach().to(dev, torch.float64).contiguous() if shift is not None else None
+        _native.peg_fwd(dtype, l, batch=B, n=n, gaps=gaps if nm1 > 0 else None, stride_gaps=gaps.stride(0) if nm1 > 0 else 0,
+                        lam_re=consts.lam_re, lam_im=consts.lam_im, M_re=consts.M_re, M_im=consts.M_im, shift=sh,
+                        R=R, O=O if nm1 > 0 else None, strideR=n * l * l, strideO=nm1 * l * l, info=info, nterms=consts.nterms)
+        ctx.consts, ctx.meta = consts, (B, n, l, dtype)
+        ctx.save_for_backward(gaps, O)
+        ctx.G_meta = (G.device, G.dtype)
+        ctx.shift_meta = (shift.device, shift.dtype) if shift is not None else None
+        ctx.info = info
+        return R, O
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gR, gO):
+        gaps, O = ctx.saved_tensors
+        B, n, l, dtype = ctx.meta
+        c = ctx.consts
+        dev = gaps.device
+        gG = gshift = None
+        if ctx.needs_input_grad[1]:
+            Z = torch.zeros(2 * l * l, dtype=torch.float64, device=dev)
+            if n > 1:
+                gRc = _engine._rows_contiguous(gR.to(dtype))
+                gOc = _engine._rows_contiguous(gO.to(dtype))
+                _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
+                                lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im, V_re=c.V_re, V_im=c.V_im,
+                                Vinv_re=c.Vinv_re, Vinv_im=c.Vinv_im, invdl_re=c.invdl_re, invdl_im=c.invdl_im, degenerate=c.deg,
+                                O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), Z=Z,
+                                nterms=c.nterms, lamfull_re=c.lamfull_re, lamfull_im=c.lamfull_im)
+            Zc = torch.view_as_complex(Z.view(l, l, 2))
+            gG = (c.Vinv.transpose(0, 1) @ Zc @ c.V.transpose(0, 1)).real      # adjoint of expm in the eigenbasis, back in G's basis
+            gG = gG.to(*ctx.G_meta)
+        if ctx.shift_meta is not None and ctx.needs_input_grad[2]:
+            gshift = gR.sum(dim=(0, 1), dtype=torch.float64).to(*ctx.shift_meta)
+        return None, gG, gshift, None
+
+
+def device_builder_available(rank: int) -> bool:
+    return torch.cuda.is_available() and rank <= _native.peg_max_ell()
+
+
+def peg_precision(gaps, G, shift=None, check=True):
+    """gaps (B, n-1) or (n-1,) on a CUDA device (float32 / float64 = the dtype of the blocks), G (l,l) and shift (l,l)
+    anywhere (they are tiny): returns (Rs, Os) on the device of `gaps`.  Differentiable wrt G and shift."""
+    single = gaps.dim() == 1
+    g2 = gaps.unsqueeze(0) if single else gaps
+    if not (g2.is_cuda and device_builder_available(G.shape[0])):
+        Gd = G.to(g2.device, g2.dtype)
+        R, O = peg_precision_torch(g2, Gd, shift.to(g2.device, g2.dtype) if shift is not None else None)
+    else:
+        consts = _EigConsts(G, g2.device)
+        if consts.cond > EIG_COND_MAX:
+            R, O = peg_precision_torch(g2, G.to(g2.device, g2.dtype), shift.to(g2.device, g2.dtype) if shift is not None else None)
+        else:
+            R, O = _PegFn.apply(g2.contiguous(), G, shift, consts)
+    return (R[0], O[0]) if single else (R, O)

@@ -38,7 +38,7 @@ extern "C" {
 
 /* kernel families: thread-per-node (sizeof(T)*ell*ell <= 400 B: fp32 ell <= 10, fp64 ell <= 7), column-split (several lanes
  * per node: fp32 ell=8, fp64 ell=4 and 8; chosen automatically for fp64 ell=8), warp-per-node with the block products on the
- * FP64 tensor path (DMMA; ell >= 8, chosen automatically for every larger block: fp32 ell >= 11, fp64 ell >= 9; fp32 data is
+ * FP64 tensor path (DMMA; ell >= 8, chosen automatically where it measured faster than lane-per-row: fp64 ell >= 10, fp32 ell >= 17; fp32 data is
  * widened to fp64 on chip) and the first-generation lane-per-row kernels (any ell <= 32; kept as a cross-check) */
 #define CRB200_AUTO 0
 #define CRB200_LANE_PER_ROW 1
@@ -156,6 +156,44 @@ typedef struct crb200_sweep_hs_args {
 int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* args, void* stream);
 int crb200_sweep_halfsolve(int dtype, int ell, const crb200_sweep_hs_args* args, void* stream);
 int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* args, void* stream);
+
+/* Precision-block builder of the LEG / PEG process.  Replaces LEGFamily.compute_PEG_precision (models.py:181-239) with the
+ * posterior shift of compute_posterior_precision (:254-268) folded in, and torch autograd through them.  The caller
+ * eigendecomposes G = V diag(lam) V^{-1} once on the host (as the reference's compute_eG does, model_utils.py:12-29) and
+ * passes lam, M_k = V[:,k] V^{-1}[k,:] (k-major, ell*ell each) as DEVICE arrays of doubles; gaps are d_g = t_{g+1} - t_g > 0.
+ * Forward writes R (batch,n,l,l) and O (batch,n-1,l,l).  Backward turns cotangents gR / gO into Z (2*l*l doubles, re/im
+ * interleaved, ACCUMULATED into -- zero it first), from which gG = Re(V^{-T} Z V^T); the cotangent of `shift` is sum_i gR_i.
+ * info (may be NULL): set to 1 if some I - A A^T was not positive definite (a non-positive gap). */
+typedef struct crb200_peg_fwd_args {
+  int batch, n;
+  const void* gaps; long long stride_gaps;             /* (batch, n-1), element type = dtype; series stride in elements */
+  const double* lam_re; const double* lam_im;
+  const double* M_re; const double* M_im;
+  const double* shift;                                 /* (l,l) added to every diagonal block, or NULL */
+  void* R; void* O; long long strideR, strideO;
+  int* info;
+  int nterms;                                          /* 0 = ell.  exp(cG) - I = Re sum_{k < nterms} (e^{c lam_k} - 1) M_k: a caller that folds
+                                                          every conjugate pair of eigenvalues into one term (M_k doubled, partner dropped)
+                                                          passes fewer than ell terms and halves the work of the expansion */
+} crb200_peg_fwd_args;
+
+typedef struct crb200_peg_bwd_args {
+  int batch, n;
+  const void* gaps; long long stride_gaps;
+  const double* lam_re; const double* lam_im; const double* M_re; const double* M_im;
+  const double* V_re; const double* V_im; const double* Vinv_re; const double* Vinv_im;   /* (l,l) row-major */
+  const double* invdl_re; const double* invdl_im;      /* 1 / (lam_j - lam_k), 0 where the pair is treated as degenerate */
+  const double* degenerate;                            /* 1.0 on the diagonal and for (numerically) equal eigenvalues, else 0.0 */
+  const void* O; long long strideO;                    /* the forward result */
+  const void* gR; const void* gO; long long stride_gR, stride_gO;
+  double* Z;
+  int nterms;                                          /* as in crb200_peg_fwd_args, for lam / M (the V, Vinv, invdl arrays are always full) */
+  const double* lamfull_re; const double* lamfull_im;  /* all ell eigenvalues, in the order of V's columns */
+} crb200_peg_bwd_args;
+
+int crb200_peg_precision_fwd(int dtype, int ell, const crb200_peg_fwd_args* args, void* stream);
+int crb200_peg_precision_bwd(int dtype, int ell, const crb200_peg_bwd_args* args, void* stream);
+int crb200_peg_max_ell(void);                          /* largest ell the builder kernels exist for (larger: host falls back to torch ops) */
 
 int crb200_version(void);
 int crb200_max_ell(void);

@@ -1,0 +1,76 @@
+"""GPU: the device precision-block builder (cyclic_gps.peg, crb200_peg_precision_fwd / _bwd) against the
+reference's formulas in torch ops with torch autograd (peg_precision_torch = compute_PEG_precision of the reference,
+models.py:181-239, plus the posterior shift :254-268), in fp64 on the CPU."""
+import pytest
+import torch
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _model_G(l, seed, noise=1.0):
+    g = torch.Generator().manual_seed(seed)
+    N = torch.tril(torch.randn((l, l), generator=g, dtype=torch.float64)) * 0.4 + noise * torch.eye(l, dtype=torch.float64)
+    A = torch.randn((l, l), generator=g, dtype=torch.float64)
+    Rm = torch.tril((A - A.T) * 0.3, diagonal=-1)
+    # (0.5 I keeps the slowest mode away from zero: 1 / gap-sized blocks are as ill-conditioned as I - A A^T, for any implementation)
+    G = N @ N.T + Rm - Rm.T + (0.5 + 1e-5) * torch.eye(l, dtype=torch.float64)
+    Bm = torch.randn((2, l), generator=g, dtype=torch.float64) * 0.5
+    shift = Bm.T @ Bm * 3.0
+    return G, shift
+
+
+@pytest.mark.parametrize("dtype,tol_f,tol_g", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 1e-4)])
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_builder_forward_and_backward_vs_torch_autograd(l, dtype, tol_f, tol_g):
+    from cyclic_gps.peg import peg_precision, peg_precision_torch
+    for (B, n, seed) in ((1, 2, 1), (3, 33, 2), (2, 100, 3), (5, 31, 4), (1, 1, 5)):
+        G, shift = _model_G(l, 10 * l + seed)
+        gen = torch.Generator().manual_seed(seed)
+        gaps = -torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64)) + 0.02
+        Gr, sr = G.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+        R0, O0 = peg_precision_torch(gaps, Gr, sr)
+        cR = torch.randn(R0.shape, generator=gen, dtype=torch.float64)
+        cR = cR + cR.transpose(-1, -2) if seed % 2 else cR            # the CR backward produces symmetric gR; test both
+        cO = torch.randn(O0.shape, generator=gen, dtype=torch.float64)
+        ((R0 * cR).sum() + (O0 * cO).sum()).backward()
+        Gd, sd = G.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+        R1, O1 = peg_precision(gaps.to(dtype).cuda(), Gd, sd)
+        assert R1.is_cuda and R1.dtype == dtype and tuple(R1.shape) == tuple(R0.shape) and tuple(O1.shape) == tuple(O0.shape)
+        assert_close(R1, R0, tol_f, f"Rs l={l} B={B} n={n}")
+        if n > 1:
+            assert_close(O1, O0, tol_f, f"Os l={l} B={B} n={n}")
+        ((R1 * cR.to(dtype).cuda()).sum() + (O1 * cO.to(dtype).cuda()).sum()).backward()
+        assert_close(sd.grad, sr.grad, tol_g, f"g shift l={l} n={n}")
+        if n > 1:
+            assert_close(Gd.grad, Gr.grad, tol_g, f"gG l={l} B={B} n={n}")
+
+
+def test_builder_small_gaps_fp32_have_no_cancellation():
+    """I - A A^T is formed from A - I (expm1), so gaps of 1e-3 keep fp32 accuracy."""
+    from cyclic_gps.peg import peg_precision, peg_precision_torch
+    G, shift = _model_G(8, 3)
+    gaps = torch.full((2, 40), 1e-3, dtype=torch.float64)
+    gaps[1] = torch.linspace(1e-3, 0.5, 40, dtype=torch.float64)
+    R0, O0 = peg_precision_torch(gaps, G, shift)
+    R1, O1 = peg_precision(gaps.float().cuda(), G, shift)
+    assert_close(R1, R0, 2e-5, "Rs small gaps")
+    assert_close(O1, O0, 2e-5, "Os small gaps")
+
+
+def test_degenerate_eigenvalues_and_regular_spacing():
+    """N = I, R = 0: G is a multiple of the identity (all eigenvalues equal) -- the divided differences fall back to the
+    derivative form."""
+    from cyclic_gps.peg import peg_precision, peg_precision_torch
+    l = 4
+    G = (1.0 + 1e-5) * torch.eye(l, dtype=torch.float64)
+    gaps = torch.ones((2, 20), dtype=torch.float64)
+    Gr = G.clone().requires_grad_(True)
+    R0, O0 = peg_precision_torch(gaps, Gr, None)
+    (R0.sum() + (O0 ** 2).sum()).backward()
+    Gd = G.clone().requires_grad_(True)
+    R1, O1 = peg_precision(gaps.cuda(), Gd, None)
+    (R1.sum() + (O1 ** 2).sum()).backward()
+    assert_close(R1, R0, 1e-11, "Rs")
+    assert_close(Gd.grad, Gr.grad, 1e-9, "gG degenerate")
