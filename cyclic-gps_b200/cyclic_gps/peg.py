@@ -117,6 +117,21 @@ class _PegFn(torch.autograd.Function):
         return None, gG, gshift, None
 
 
+_consts_cache = {}
+
+
+def _consts_for(G, dev):
+    """The eigendecomposition is redone only when G changes: the key is the tensor's identity and version counter
+    (an optimiser step or register_model_matrices_from_params bumps it)."""
+    key = (G.data_ptr(), G._version, tuple(G.shape), G.dtype, str(dev))
+    hit = _consts_cache.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    c = _EigConsts(G, dev)
+    _consts_cache["last"] = (key, c)
+    return c
+
+
 def device_builder_available(rank: int) -> bool:
     return torch.cuda.is_available() and rank <= _native.peg_max_ell()
 
@@ -130,7 +145,7 @@ def peg_precision(gaps, G, shift=None, check=True):
         Gd = G.to(g2.device, g2.dtype)
         R, O = peg_precision_torch(g2, Gd, shift.to(g2.device, g2.dtype) if shift is not None else None)
     else:
-        consts = _EigConsts(G, g2.device)
+        consts = _consts_for(G, g2.device)
         if consts.cond > EIG_COND_MAX:
             R, O = peg_precision_torch(g2, G.to(g2.device, g2.dtype), shift.to(g2.device, g2.dtype) if shift is not None else None)
         else:
