@@ -23,6 +23,7 @@
 // tiles of a persistent warp, one atomicAdd per entry and warp at the end.  The host finishes gG = Re(V^{-T} Z V^T).
 #pragma once
 #include "cr_common.cuh"
+#include "cr_tpn_common.cuh"   // record_stride
 
 namespace crb200 {
 
@@ -129,6 +130,28 @@ __device__ __forceinline__ void peg_load_block(T (&M)[L][L], const T* __restrict
   for (int r = 0; r < L; ++r)
 #pragma unroll
     for (int q = 0; q < L; ++q) M[r][q] = g[r * L + q];
+}
+
+template <typename T, int L>
+__device__ __forceinline__ void peg_load_row(T (&v)[L], const T* __restrict__ g, const bool vec_ok) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  if constexpr ((L % VE) == 0) {
+    if (vec_ok) {
+#pragma unroll
+      for (int i = 0; i < L; i += VE) {
+        if constexpr (sizeof(T) == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(g + i));
+          v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        } else {
+          const double2 t = __ldg(reinterpret_cast<const double2*>(g + i));
+          v[i] = t.x; v[i + 1] = t.y;
+        }
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < L; ++i) v[i] = __ldg(g + i);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -287,6 +310,11 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_bwd_kernel(const PegBwdArg
   double accZ[SLOTS];
 #pragma unroll
   for (int i = 0; i < SLOTS; ++i) accZ[i] = 0.0;
+  // per-thread record [ A | B ] behind the constants; the stride keeps the threads of a warp on different banks
+  constexpr int RS = record_stride<CT>(2 * BS, BS);
+  CT* sA = reinterpret_cast<CT*>(smem_raw + align16(sizeof(PegBwdConsts<CT, L>))) + (size_t)threadIdx.x * RS;
+  CT* sB = sA + BS;
+  const int ncols = a.nterms > 0 ? a.nterms : L;     // columns j of Z the kernel produces (the caller mirrors the conjugate ones)
 
   for (long long vt = (long long)blockIdx.x * (kPegThreads / 32) + warp; vt < ntiles; vt += nwarps) {
     const int b = (int)(vt / tiles_per_series);
@@ -302,75 +330,104 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_bwd_kernel(const PegBwdArg
       const T* gR = static_cast<const T*>(a.gR) + (size_t)b * a.stride_gR;
       const T* gO = static_cast<const T*>(a.gO) + (size_t)b * a.stride_gO;
       const T* Og = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
+      const T* Ug = gR + (size_t)(g + 1) * BS;       // U = gR_{g+1}
+      const T* Wg = gR + (size_t)g * BS;             // W = gR_g
+      const T* Hg = gO + (size_t)g * BS;             // H = gO_g
+      const bool vR = is_aligned16(gR), vH = is_aligned16(gO);
       c = CT(-0.5) * (CT) static_cast<const T*>(a.gaps)[(size_t)b * a.stride_gaps + g];
-      CT A[L][L], Bm[L][L];
-      peg_expm_minus_I<CT, L>(A, &S->f, c, a.nterms > 0 ? a.nterms : L);
-#pragma unroll
-      for (int r = 0; r < L; ++r) A[r][r] += CT(1);
-      peg_load_block<T, L>(Bm, Og + (size_t)g * BS, is_aligned16(Og));
-#pragma unroll
-      for (int r = 0; r < L; ++r)
-#pragma unroll
-        for (int q = 0; q < L; ++q) Bm[r][q] = -Bm[r][q];                 // B = -O_g
-      CT X1[L][L], Y3[L][L];
+      // A and B = -O_g live in this thread's shared-memory record (rows are re-read many times; registers hold X1 and Y3)
       {
-        // X1 = (Us - H A^T) B - H,   Us = U + U^T,  U = gR_{g+1}
-        CT U[L][L], H[L][L];
-        peg_load_block<T, L>(U, gR + (size_t)(g + 1) * BS, is_aligned16(gR));
-        peg_load_block<T, L>(H, gO + (size_t)g * BS, is_aligned16(gO));
+        CT A[L][L];
+        peg_expm_minus_I<CT, L>(A, &S->f, c, a.nterms > 0 ? a.nterms : L);
 #pragma unroll
         for (int r = 0; r < L; ++r) {
-          CT tt[L];
-#pragma unroll
-          for (int q = 0; q < L; ++q) {
-            CT s = U[r][q] + U[q][r];
-#pragma unroll
-            for (int k = 0; k < L; ++k) s = fma(-H[r][k], A[q][k], s);
-            tt[q] = s;
-          }
-#pragma unroll
-          for (int j = 0; j < L; ++j) {
-            CT s = -H[r][j];
-#pragma unroll
-            for (int q = 0; q < L; ++q) s = fma(tt[q], Bm[q][j], s);
-            X1[r][j] = s;
-          }
+          A[r][r] += CT(1);
+          sts_row<CT, L>(sA + r * L, A[r]);
         }
-        // Y3 = A^T X1 + X2,   X2 = Ws + (Ws A^T - H^T) B,   Ws = W + W^T,  W = gR_g   (W reuses the registers of U)
-        peg_load_block<T, L>(U, gR + (size_t)g * BS, is_aligned16(gR));
+        peg_load_block<T, L>(A, Og + (size_t)g * BS, is_aligned16(Og));
 #pragma unroll
         for (int r = 0; r < L; ++r) {
-          CT tt[L], ws[L];
 #pragma unroll
-          for (int q = 0; q < L; ++q) ws[q] = U[r][q] + U[q][r];
-#pragma unroll
-          for (int q = 0; q < L; ++q) {
-            CT s = -H[q][r];
-#pragma unroll
-            for (int k = 0; k < L; ++k) s = fma(ws[k], A[q][k], s);
-            tt[q] = s;
-          }
-#pragma unroll
-          for (int j = 0; j < L; ++j) {
-            CT s = ws[j];
-#pragma unroll
-            for (int q = 0; q < L; ++q) s = fma(tt[q], Bm[q][j], s);
-#pragma unroll
-            for (int k = 0; k < L; ++k) s = fma(A[k][r], X1[k][j], s);
-            Y3[r][j] = s;
-          }
+          for (int q = 0; q < L; ++q) A[r][q] = -A[r][q];
+          sts_row<CT, L>(sB + r * L, A[r]);
         }
       }
-      // gA = X1 + B Y3
+      CT Y3[L][L];
+      // X1 = (Us - H A^T) B - H,  Us = U + U^T   (rows of U, H stream from global memory / L1; gA holds X1)
 #pragma unroll
-      for (int r = 0; r < L; ++r)
+      for (int r = 0; r < L; ++r) {
+        CT hrow[L], us[L], tt[L];
+        peg_load_row<T, L>(hrow, Hg + r * L, vH);
+        peg_load_row<T, L>(us, Ug + r * L, vR);
+#pragma unroll
+        for (int q = 0; q < L; ++q) us[q] += __ldg(Ug + q * L + r);
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+          CT arow[L];
+          lds_row<CT, L>(arow, sA + q * L);
+          CT sacc = us[q];
+#pragma unroll
+          for (int k = 0; k < L; ++k) sacc = fma(-hrow[k], arow[k], sacc);
+          tt[q] = sacc;
+        }
+#pragma unroll
+        for (int j = 0; j < L; ++j) gA[r][j] = -hrow[j];
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+          CT brow[L];
+          lds_row<CT, L>(brow, sB + q * L);
+#pragma unroll
+          for (int j = 0; j < L; ++j) gA[r][j] = fma(tt[q], brow[j], gA[r][j]);
+        }
+      }
+      // Y3 = X2 + A^T X1,  X2 = Ws + (Ws A^T - H^T) B,  Ws = W + W^T
+#pragma unroll
+      for (int r = 0; r < L; ++r) {
+        CT ws[L], tt[L];
+        peg_load_row<T, L>(ws, Wg + r * L, vR);
+#pragma unroll
+        for (int q = 0; q < L; ++q) ws[q] += __ldg(Wg + q * L + r);
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+          CT arow[L];
+          lds_row<CT, L>(arow, sA + q * L);
+          CT sacc = -(CT)__ldg(Hg + q * L + r);
+#pragma unroll
+          for (int k = 0; k < L; ++k) sacc = fma(ws[k], arow[k], sacc);
+          tt[q] = sacc;
+        }
+#pragma unroll
+        for (int j = 0; j < L; ++j) Y3[r][j] = ws[j];
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+          CT brow[L];
+          lds_row<CT, L>(brow, sB + q * L);
+#pragma unroll
+          for (int j = 0; j < L; ++j) Y3[r][j] = fma(tt[q], brow[j], Y3[r][j]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        CT arow[L];
+        lds_row<CT, L>(arow, sA + k * L);
+#pragma unroll
+        for (int r = 0; r < L; ++r)
+#pragma unroll
+          for (int j = 0; j < L; ++j) Y3[r][j] = fma(arow[r], gA[k][j], Y3[r][j]);
+      }
+      // gA = X1 + B Y3   (in place, row by row)
+#pragma unroll
+      for (int r = 0; r < L; ++r) {
+        CT brow[L];
+        lds_row<CT, L>(brow, sB + r * L);
 #pragma unroll
         for (int j = 0; j < L; ++j) {
-          CT s = X1[r][j];
+          CT sacc = gA[r][j];
 #pragma unroll
-          for (int k = 0; k < L; ++k) s = fma(Bm[r][k], Y3[k][j], s);
-          gA[r][j] = s;
+          for (int k = 0; k < L; ++k) sacc = fma(brow[k], Y3[k][j], sacc);
+          gA[r][j] = sacc;
         }
+      }
     }
     // Daleckii-Krein in the eigenbasis: T = gA^T V (column j), Y_kj = sum_m Vinv[k][m] T[m][j], Z_jk = Y_kj Phi_jk
     double ere[L], eim[L];                                         // e^{c lam_k} in fp64 (see PegBwdConsts)
@@ -385,6 +442,7 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_bwd_kernel(const PegBwdArg
     }
 #pragma unroll
     for (int j = 0; j < L; ++j) {
+      if (j >= ncols) break;                                         // uniform
       CT Tre[L], Tim[L];
 #pragma unroll
       for (int m = 0; m < L; ++m) {
@@ -445,7 +503,7 @@ cudaError_t launch_peg_fwd(const PegFwdArgs& a, cudaStream_t stream) {
 
 template <typename T, int L>
 cudaError_t launch_peg_bwd(const PegBwdArgs& a, cudaStream_t stream) {
-  const size_t smem = sizeof(PegBwdConsts<T, L>);
+  const size_t smem = align16(sizeof(PegBwdConsts<T, L>)) + (size_t)kPegThreads * record_stride<T>(2 * L * L, L * L) * sizeof(T);
   static std::atomic<unsigned char> attr_done[kMaxDevices];
   if (cudaError_t e = ensure_dynamic_smem(cr_peg_bwd_kernel<T, L>, (int)smem, attr_done); e != cudaSuccess) return e;
   if (a.n < 2 || a.batch <= 0) return cudaSuccess;

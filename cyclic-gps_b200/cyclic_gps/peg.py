@@ -41,21 +41,32 @@ class _EigConsts:
         l = G.shape[0]
         Gc = G.detach().to(torch.float64).cpu()
         lam, V = torch.linalg.eig(Gc)
-        Vinv = torch.linalg.inv(V)
         self.cond = float(torch.linalg.cond(V))
-        M = torch.einsum("rk,kc->krc", V, Vinv).reshape(l, l * l)
-        # the expansion exp(cG) - I = Re sum_k (e^{c lam_k} - 1) M_k only needs one member of every conjugate pair (doubled);
-        # real eigenvalues count once.  Terms are packed to the front, the rest is padding that is never read.
+        # Order the spectrum as [eigenvalues with Im > 0 | real eigenvalues | conjugates of the first group] and make the
+        # conjugate columns of V exact conjugates (G is real): the expansion of exp(cG) - I then only needs the first
+        # `nterms` terms (complex ones doubled), and the kernel only produces the rows j < nterms of Z -- the others follow
+        # from Z[j', k'] = conj(Z[j, k]) with ' = conjugate partner.
         tol = 1e-12 * float(lam.abs().max().clamp_min(1e-300))
-        keep = [k for k in range(l) if lam[k].imag > tol] + [k for k in range(l) if abs(float(lam[k].imag)) <= tol]
-        n_neg = sum(1 for k in range(l) if lam[k].imag < -tol)
-        if n_neg == sum(1 for k in range(l) if lam[k].imag > tol):
-            w = torch.tensor([2.0 if lam[k].imag > tol else 1.0 for k in keep], dtype=torch.float64)
-            lam_t = torch.cat([lam[keep], torch.zeros(l - len(keep), dtype=lam.dtype)])
-            M_t = torch.cat([M[keep] * w.unsqueeze(1), torch.zeros((l - len(keep), l * l), dtype=M.dtype)])
-            self.nterms = len(keep)
-        else:                                           # (not a conjugate-closed spectrum: cannot happen for real G; keep everything)
-            lam_t, M_t, self.nterms = lam, M, l
+        pos = [k for k in range(l) if float(lam[k].imag) > tol]
+        real = [k for k in range(l) if abs(float(lam[k].imag)) <= tol]
+        if len(pos) + len(real) + len(pos) == l:
+            lam = torch.cat([lam[pos], lam[real].real.to(lam.dtype), lam[pos].conj()])
+            Vr = V[:, real]
+            if len(real):                               # real eigenvalue -> real eigenvector (remove the arbitrary phase)
+                piv = Vr.abs().argmax(dim=0)
+                ph = Vr[piv, torch.arange(len(real))]
+                Vr = (Vr * (ph.conj() / ph.abs())).real.to(V.dtype)
+            V = torch.cat([V[:, pos], Vr, V[:, pos].conj()], dim=1)
+            self.nterms = len(pos) + len(real)
+            self.partner = list(range(self.nterms, l)) + list(range(len(pos), self.nterms)) + list(range(len(pos)))
+            weights = torch.tensor([2.0] * len(pos) + [1.0] * len(real), dtype=torch.float64)
+        else:                                           # (spectrum not closed under conjugation: cannot happen for a real G)
+            self.nterms, self.partner, weights = l, None, torch.ones(l, dtype=torch.float64)
+        Vinv = torch.linalg.inv(V)
+        M = torch.einsum("rk,kc->krc", V, Vinv).reshape(l, l * l)
+        nt = self.nterms
+        lam_t = torch.cat([lam[:nt], torch.zeros(l - nt, dtype=lam.dtype)])
+        M_t = torch.cat([M[:nt] * weights.unsqueeze(1), torch.zeros((l - nt, l * l), dtype=M.dtype)])
         dl = lam.unsqueeze(1) - lam.unsqueeze(0)
         deg = dl.abs() <= 1e-9 * lam.abs().max().clamp_min(1e-300)
         invdl = torch.where(deg, torch.zeros_like(dl), 1.0 / torch.where(deg, torch.ones_like(dl), dl))
@@ -110,6 +121,11 @@ class _PegFn(torch.autograd.Function):
                                 O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), Z=Z,
                                 nterms=c.nterms, lamfull_re=c.lamfull_re, lamfull_im=c.lamfull_im)
             Zc = torch.view_as_complex(Z.view(l, l, 2))
+            if c.partner is not None and c.nterms < l:      # rows the kernel skipped: Z[j', k'] = conj(Z[j, k])
+                part = torch.tensor(c.partner, device=dev)
+                mirrored = Zc[part][:, part].conj()
+                rows = torch.arange(l, device=dev).unsqueeze(1) < c.nterms
+                Zc = torch.where(rows, Zc, mirrored)
             gG = (c.Vinv.transpose(0, 1) @ Zc @ c.V.transpose(0, 1)).real      # adjoint of expm in the eigenbasis, back in G's basis
             gG = gG.to(*ctx.G_meta)
         if ctx.shift_meta is not None and ctx.needs_input_grad[2]:
@@ -121,9 +137,9 @@ _consts_cache = {}
 
 
 def _consts_for(G, dev):
-    """The eigendecomposition is redone only when G changes: the key is the tensor's identity and version counter
-    (an optimiser step or register_model_matrices_from_params bumps it)."""
-    key = (G.data_ptr(), G._version, tuple(G.shape), G.dtype, str(dev))
+    """The eigendecomposition is redone only when G changes: the key is G's CONTENT (l x l numbers; a model rebuilds the
+    tensor from its parameters on every call, so identity or version counters say nothing)."""
+    key = (G.detach().to("cpu", torch.float64).numpy().tobytes(), tuple(G.shape), str(dev))
     hit = _consts_cache.get("last")
     if hit is not None and hit[0] == key:
         return hit[1]
