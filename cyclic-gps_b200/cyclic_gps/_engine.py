@@ -26,6 +26,19 @@ class NotPositiveDefiniteError(RuntimeError):
     cyclic_reduction.py:227,306,429; the jitter retry is not replicated)."""
 
 
+class NanError(RuntimeError):
+    """A diagonal block contains NaNs (gpytorch's NanError in the reference's psd_safe_cholesky)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    """Jitter was added to the diagonal to make a block positive definite (gpytorch's NumericalWarning)."""
+
+
+def default_jitter(dtype) -> float:
+    """gpytorch.settings.cholesky_jitter defaults used by the reference's psd_safe_cholesky (cyclic_reduction.py:13, :227)."""
+    return 1e-6 if dtype == torch.float32 else 1e-8
+
+
 def require_cuda() -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("the cyclic-reduction engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -97,9 +110,12 @@ class FactorPack:
             k = int(bad[0])
             flat = 0x7FFFFFFF - int(info[k])
             E = counts(self.ms[k])[0]
+            tail = ""
+            if getattr(self, "jitter_exhausted", None):
+                tail = f" after repeatedly adding jitter up to {self.jitter_exhausted:.1e}"
             raise NotPositiveDefiniteError(
                 f"cyclic reduction: diagonal block not positive definite at level {k} "
-                f"(series {flat // E}, even node {flat % E}, i.e. reduced row {2 * (flat % E)})")
+                f"(series {flat // E}, even node {flat % E}, i.e. reduced row {2 * (flat % E)})" + tail)
 
 
 class DeferredCheck:
@@ -227,12 +243,18 @@ def _rows_contiguous(t):
 
 def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *, keep_factors: bool,
                   want_logdet: bool = True, nlevels: Optional[int] = None,
-                  halo_O: Optional[torch.Tensor] = None) -> FactorPack:
+                  halo_O: Optional[torch.Tensor] = None, jitter=None) -> FactorPack:
     """Run CR levels 0..nlevels-1 (default: all, down to the last 1x1 system).
 
     R (B,n,l,l), O (B,n-1,l,l) [any strided batch axis, rows contiguous], y (B,n,l) or None.
     The level loop runs inside libcrb200 (crb200_sweep_fwd); when bench.py's launch tracer is
-    active the per-level entries are used instead so that every launch can be timed."""
+    active the per-level entries are used instead so that every launch can be timed.
+
+    jitter = (base, max_tries): error-recovery path that mirrors gpytorch's psd_safe_cholesky as the reference calls it
+    once per level (cyclic_reduction.py:227, :306, :429): levels run one at a time; when a level reports a block that
+    is not positive definite, `base * 10**i` (i = 0..max_tries-1) is added to the diagonal of ALL even blocks of that
+    level (the whole batch handed to that Cholesky call) and the level is redone, with a NumericalWarning per try;
+    NotPositiveDefiniteError after the last try, NanError if the blocks contain NaNs.  One host sync per level."""
     B, n, ell = R.shape[0], R.shape[1], R.shape[2]
     dtype, dev = R.dtype, R.device
     bs = ell * ell
@@ -285,7 +307,9 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
     sR, sO = R.stride(0), (O.stride(0) if O.shape[1] > 0 else 0)
     sy = y.stride(0) if y is not None else 0
 
-    if not _native.tracing():
+    if jitter is not None and halo:
+        raise ValueError("the jitter ladder is not available for halo (chunk-partitioned) sweeps")
+    if not _native.tracing() and jitter is None:
         _native.sweep_fwd(dtype, ell, batch=B, n=n, nlevels=L, R=R, O=O if n > 1 else None, y=y,
                           strideR=sR, strideO=sO, stridey=sy,
                           D=pack.D_flat, F=pack.F_flat if (keep_factors and pack.F_flat.numel()) else None,
@@ -311,7 +335,37 @@ def forward_sweep(R: torch.Tensor, O: torch.Tensor, y: Optional[torch.Tensor], *
             if halo:
                 fields.update(O_halo=cur_halo, G_halo=pack.G_halo[k] if keep_factors else None, On_halo=On_h[slot], Rh_acc=Rh, yh_acc=yh)
                 cur_halo = On_h[slot]
+            snap = None
+            if jitter is not None:                   # the scalars of a failed attempt must not stay in the accumulators
+                snap = (acc_ld.clone() if acc_ld is not None else None, acc_mh.clone() if acc_mh is not None else None)
             _native.level_fwd(dtype, ell, **fields)
+            if jitter is not None and int(pack.info[k]) != 0:
+                base, tries = jitter
+                Rb = cur_R if k == 0 else cur_R[:B * m].view(B, m, ell, ell)
+                if bool(torch.isnan(Rb[:, 0::2]).any()):
+                    raise NanError(f"cyclic reduction: NaN in a diagonal block at level {k}")
+                Rj = Rb.contiguous().clone() if k == 0 else Rb.clone()
+                prev, ok = 0.0, False
+                for i in range(tries):
+                    new = base * (10 ** i)
+                    Rj[:, 0::2].diagonal(dim1=-2, dim2=-1).add_(new - prev)
+                    prev = new
+                    import warnings
+                    warnings.warn(f"cyclic reduction level {k}: block not positive definite, added jitter of {new:.1e} to the diagonal",
+                                  NumericalWarning)
+                    pack.info[k:k + 1].zero_()
+                    if snap[0] is not None:
+                        acc_ld.copy_(snap[0])
+                    if snap[1] is not None:
+                        acc_mh.copy_(snap[1])
+                    fields.update(R=Rj, strideR=m * bs)
+                    _native.level_fwd(dtype, ell, **fields)
+                    if int(pack.info[k]) == 0:
+                        ok = True
+                        break
+                if not ok:
+                    pack.jitter_exhausted = prev
+                    pack.check()
             cur_R, cur_O, cur_y = fields["Rn"], fields["On"], fields["yn"]
             sR, sO, sy = o * bs, max(o - 1, 0) * bs, o * ell
     if slots == 1:

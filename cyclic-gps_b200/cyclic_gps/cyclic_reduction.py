@@ -13,8 +13,9 @@ Differences from the reference, all additive:
     never a CPU compute path; without a CUDA device the calls raise);
   * ``mahal_and_det`` and ``det(decompose(...))`` carry a hand-written backward (closed-form
     gradients from a back-solve + selected inverse) instead of a torch autograd tape;
-  * a non-positive-definite diagonal block raises ``NotPositiveDefiniteError`` (no jitter
-    retry; reference: gpytorch ``psd_safe_cholesky``, cyclic_reduction.py:227,306,429).
+  * a non-positive-definite diagonal block goes through the reference's jitter ladder (gpytorch
+    ``psd_safe_cholesky``, cyclic_reduction.py:227,306,429; see ``JITTER``) and raises
+    ``NotPositiveDefiniteError`` (alias ``NotPSDError``) after the last try.
 
 ``np`` and ``torch`` are re-exported on purpose: the reference's own tests rely on
 ``from cyclic_gps.cyclic_reduction import *`` providing them
@@ -27,9 +28,30 @@ import numpy as np  # noqa: F401  (re-exported, see module docstring)
 import torch
 
 from . import _engine
-from ._engine import NotPositiveDefiniteError  # noqa: F401
+from ._engine import NanError, NotPositiveDefiniteError, NumericalWarning  # noqa: F401
 
-JITTER = None  # reference module attribute (cyclic_reduction.py:13); no jitter is ever added here
+NotPSDError = NotPositiveDefiniteError   # the name the reference's callers catch (gpytorch.utils.errors.NotPSDError)
+
+# Reference module attribute (cyclic_reduction.py:13), handed to psd_safe_cholesky as `jitter`: None = gpytorch's default
+# (1e-6 in float32, 1e-8 in float64).  When a forward sweep reports a block that is not positive definite, the sweep is
+# redone level by level with the reference's jitter ladder (JITTER * 10**i, i < CHOLESKY_MAX_TRIES, added to the diagonal of
+# every even block of the failing level; a NumericalWarning per try), and NotPositiveDefiniteError is raised after the last
+# try -- _engine.forward_sweep(jitter=...).  CHOLESKY_MAX_TRIES = 0 switches the retry off.
+JITTER = None
+CHOLESKY_MAX_TRIES = 3
+
+
+def _forward_checked(R, O, y, **kw):
+    """Forward sweep + the reference's error contract: fast path first; on a non-positive-definite report the jitter ladder."""
+    pack = _engine.forward_sweep(R, O, y, **kw)
+    try:
+        pack.check()
+        return pack
+    except NotPositiveDefiniteError:
+        if CHOLESKY_MAX_TRIES <= 0:
+            raise
+    base = JITTER if JITTER is not None else _engine.default_jitter(R.dtype)
+    return _engine.forward_sweep(R, O, y, jitter=(base, CHOLESKY_MAX_TRIES), **kw)
 
 
 # ---------------------------------------------------------------------------------------
@@ -197,8 +219,7 @@ def decompose_step(Rs, Os):
     batched, caller = Rs.dim() == 4, Rs.device
     R = _batched(_dev(Rs, dev), batched)
     O = _batched(_dev(Os, dev), batched)
-    pack = _engine.forward_sweep(R, O, None, keep_factors=True, want_logdet=False, nlevels=1)
-    pack.check()
+    pack = _forward_checked(R, O, None, keep_factors=True, want_logdet=False, nlevels=1)
     B, ell = R.shape[0], R.shape[2]
     m = R.shape[1]
     E, o, g = _engine.counts(m)
@@ -219,8 +240,7 @@ def _decompose_impl(Rs, Os):
     batched, caller = Rs.dim() == 4, Rs.device
     R = _batched(_dev(Rs, dev), batched)
     O = _batched(_dev(Os, dev), batched)
-    pack = _engine.forward_sweep(R, O, None, keep_factors=True)
-    pack.check()
+    pack = _forward_checked(R, O, None, keep_factors=True)
     ell = R.shape[2]
     z = torch.empty((R.shape[0], 0, ell, ell), dtype=R.dtype, device=dev)
     c = lambda t: _to_caller(t, batched, caller)
@@ -390,12 +410,12 @@ class _MahalAndDetFn(torch.autograd.Function):
         O = _batched(_dev(Os, dev), batched)
         X = _batched(_dev(x, dev, Rs.dtype), batched)
         need = any(ctx.needs_input_grad[:3])
-        pack = _engine.forward_sweep(R, O, X, keep_factors=need)
         if need and not EAGER_PD_CHECK:
-            ctx.deferred = _engine.DeferredCheck([pack])
+            pack = _engine.forward_sweep(R, O, X, keep_factors=need)
+            ctx.deferred = _engine.DeferredCheck([pack])         # (no jitter retry in the deferred mode)
         else:
             ctx.deferred = None
-            pack.check()
+            pack = _forward_checked(R, O, X, keep_factors=need)
         ctx.pack = pack if need else None
         ctx.batched, ctx.devs = batched, (Rs.device, Os.device, x.device)
         mh, ld = pack.mahal.to(Rs.dtype), pack.logdet.to(Rs.dtype)

@@ -459,3 +459,57 @@ def test_graphed_mahal_and_det_replays(l, n, dtype, batch):
         for a, b_, name in ((mh, mm, "mahal"), (ld, dd, "logdet"), (gR, Rr.grad, "gR"), (gO, Or.grad, "gO"), (gx, xr.grad, "gx")):
             assert_close(a, b_, tol, f"graphed {name} seed {seed}")
         g.check()
+
+
+def test_jitter_ladder_like_psd_safe_cholesky():
+    """Error-recovery parity with the reference's psd_safe_cholesky calls (cyclic_reduction.py:227,306,429; gpytorch's ladder
+    jitter * 10**i on the whole batch of a level): a barely indefinite even block is repaired by the first rung, a badly
+    indefinite one raises NotPositiveDefiniteError (= NotPSDError) after three warnings, NaNs raise NanError."""
+    import warnings
+    c = cr()
+    R, O, x = leg_inputs(3, 40, torch.float64, seed=11)
+    eye = torch.eye(3, dtype=torch.float64)
+    # (i) a single block whose smallest eigenvalue is -3e-9: the factorisation fails, the first rung (+1e-8) repairs it
+    R1 = R[4:5] - (torch.linalg.eigvalsh(R[4]).min() + 3e-9) * eye
+    O1 = O[:0]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        mm, dd = c.mahal_and_det(R1.cuda(), O1.cuda(), x[:1].cuda())
+        dec = c.decompose(R1.cuda(), O1.cuda())
+    assert sum(issubclass(i.category, c.NumericalWarning) for i in w) == 2            # one rung per call
+    d_o = orc.factor(R1 + 1e-8 * eye, O1)                                              # what psd_safe_cholesky factorises
+    assert_close(mm, orc.mahal(d_o, x[:1]), 1e-6, "mahal after jitter")
+    assert_close(dd, orc.logdet(d_o), 1e-7, "logdet after jitter")
+    assert_close(dec[1][0], d_o[1][0], 1e-6, "D[0] after jitter")
+    # (ii) one level of a longer system: the jitter goes onto EVERY even block of the level, as in the reference's batched call
+    R3 = R[:3].clone()
+    R3[2] -= (torch.linalg.eigvalsh(R3[2]).min() + 3e-9) * eye
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        (m3, K, F, G), (Rn, On) = c.decompose_step(R3.cuda(), O[:2].cuda())
+    assert sum(issubclass(i.category, c.NumericalWarning) for i in w) == 1
+    Rj = R3.clone()
+    Rj[0::2] += 1e-8 * eye
+    (_, K2, F2, G2), (Rn2, _) = orc.level_step(Rj, O[:2])
+    assert_close(K[0], K2[0], 1e-12, "K of the healthy even block carries the jitter too")
+    assert_close(F, F2, 1e-12, "F")
+    assert_close(G, G2, 1e-5, "G (through the repaired block)")
+    # hopeless: three rungs, then the error (at level 1: the bad block is an odd row of level 0)
+    Rc = R.clone()
+    Rc[1] -= 10.0 * torch.eye(3, dtype=torch.float64)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(c.NotPSDError, match="level 1.*jitter up to 1.0e-06"):
+            c.mahal_and_det(Rc.cuda(), O.cuda(), x.cuda())
+    assert sum(issubclass(i.category, c.NumericalWarning) for i in w) == 3
+    # fp32 default ladder starts at 1e-6; JITTER overrides it; CHOLESKY_MAX_TRIES = 0 switches the retry off
+    c.CHOLESKY_MAX_TRIES = 0
+    try:
+        with pytest.raises(c.NotPositiveDefiniteError):
+            c.mahal_and_det(R1.cuda(), O1.cuda(), x[:1].cuda())
+    finally:
+        c.CHOLESKY_MAX_TRIES = 3
+    Rn = R.clone()
+    Rn[6, 0, 0] = float("nan")
+    with pytest.raises(c.NanError):
+        c.decompose(Rn.cuda(), O.cuda())
