@@ -501,7 +501,7 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
         del Rb, Ob
 
     copy_stream = torch.cuda.Stream(device=dev)
-    nchunk = 4 if (B % 4 == 0 and B >= 64) else 1
+    nchunk = args.e2e_chunks if (B % args.e2e_chunks == 0 and B >= 64) else 1
     bsz = B // nchunk
 
     def e2e_step():
@@ -632,6 +632,7 @@ def main():
     ap.add_argument("--dtype", default=WORKLOAD["dtype"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="e2e: chunks of series whose H2D copies overlap the previous chunk's compute")
     ap.add_argument("--no-long", action="store_true", help="skip the long_series object (configs[3])")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling run of configs[1]")
     ap.add_argument("--no-parity", action="store_true", help="long series: skip the parity block")

@@ -158,7 +158,7 @@ __device__ __forceinline__ void peg_load_row(T (&v)[L], const T* __restrict__ g,
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int L>
-__global__ void __launch_bounds__(kPegThreads) cr_peg_fwd_kernel(const PegFwdArgs a) {
+__global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fwd_kernel(const PegFwdArgs a) {
   using CT = T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PegConsts<CT, L>* S = reinterpret_cast<PegConsts<CT, L>*>(smem_raw);
@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_fwd_kernel(const PegFwdArg
   const bool real = g >= 0 && g <= n - 2;
   const T* gaps = static_cast<const T*>(a.gaps) + (size_t)b * a.stride_gaps;
 
-  CT Pm1[L][L], Qm1[L][L];                                      // P - I (-> row g + 1), Q - I (-> row g)
+  CT Pm1[L][L], Qm1[L][L];                  // P - I (-> row g + 1), Q - I (-> row g): symmetric, only the lower triangles (q <= r) are formed
 #pragma unroll
   for (int r = 0; r < L; ++r)
 #pragma unroll
-    for (int q = 0; q < L; ++q) Pm1[r][q] = Qm1[r][q] = CT(0);
+    for (int q = 0; q <= r; ++q) Pm1[r][q] = Qm1[r][q] = CT(0);
   bool bad = false;
   if (real) {
     const CT c = CT(-0.5) * (CT)gaps[g];
@@ -234,11 +234,11 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_fwd_kernel(const PegFwdArg
         Bm[r][q] = s * inv[r];
       }
     }
-    // P - I = B A^T,  Q - I = A^T B   (A = I + D)
+    // P - I = B A^T,  Q - I = A^T B   (A = I + D); both are symmetric
 #pragma unroll
     for (int r = 0; r < L; ++r)
 #pragma unroll
-      for (int q = 0; q < L; ++q) {
+      for (int q = 0; q <= r; ++q) {
         CT sp = Bm[r][q], sq = Bm[r][q];                         // the identity part of A
 #pragma unroll
         for (int k = 0; k < L; ++k) {
@@ -264,9 +264,10 @@ __global__ void __launch_bounds__(kPegThreads) cr_peg_fwd_kernel(const PegFwdArg
 #pragma unroll
   for (int r = 0; r < L; ++r)
 #pragma unroll
-    for (int q = 0; q < L; ++q) {
-      const CT left = __shfl_up_sync(0xffffffffu, Pm1[r][q], 1);
-      Rr[r][q] = (r == q ? CT(1) : CT(0)) + left + Qm1[r][q] + S->shift[r * L + q];
+    for (int q = 0; q <= r; ++q) {
+      const CT sym = __shfl_up_sync(0xffffffffu, Pm1[r][q], 1) + Qm1[r][q];
+      Rr[r][q] = (r == q ? CT(1) : CT(0)) + sym + S->shift[r * L + q];
+      if (q < r) Rr[q][r] = sym + S->shift[q * L + r];
     }
   if (lane >= 1 && g <= n - 1) {
     T* Rg = static_cast<T*>(a.R) + (size_t)b * a.strideR + (size_t)g * (L * L);
