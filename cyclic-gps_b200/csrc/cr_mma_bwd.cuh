@@ -28,7 +28,8 @@ struct MmaBwdCfg {
   static constexpr int VEC = 4 * LP;                          // x_e | w~_e | w_{2e} | spare
   static constexpr int REC = 5 * BLK + VEC;                   // doubles per node
   static constexpr int LEFT = BLK + VEC;                      // record of the left neighbour of warp 0: S~_d[e0-1], w~_{e0-1}
-  static constexpr int W = LP <= 24 ? 8 : 4;                  // warps (= nodes) per CTA
+  // warps (= nodes) per CTA, chosen so that TWO CTAs fit on an SM (their load / compute / store phases then overlap; see cr_mma_fwd.cuh)
+  static constexpr int W = LP <= 16 ? 8 : (LP <= 24 ? 3 : 2);
   static constexpr int NT = W;
   static constexpr size_t SMEM = (size_t)(LEFT + W * REC) * sizeof(double);
   static constexpr int MIN_CTAS = (2 * (SMEM + 1024) <= 227 * 1024) ? 2 : 1;

@@ -16,8 +16,8 @@
 // read-only halo (its B and G x are needed by the last owned node; it skips everything else).  The only exchange
 // between warps is B / G x of the right neighbour through shared memory, handed over on a named barrier per pair of
 // neighbouring warps (no CTA-wide barrier: the warps of a CTA drift apart and cover each other's serial phases).
-// Per node shared memory holds four padded blocks of doubles, each used several times:
-//   S0: R_even -> K -> Ki      S2: O_right -> F      S3: O_left -> G -> B      S4: R_odd
+// Per node shared memory holds three padded blocks of doubles, each used several times (the halo node two):
+//   S0: R_even -> K -> Ki -> R_odd (staged once Ki has been consumed)      S2: O_right -> F      S3: O_left -> G -> B
 // O~ and R~ leave straight from the accumulator fragments; K, F, G leave from shared memory as coalesced rows.
 #pragma once
 #include "cr_level_fwd.cuh"
@@ -31,10 +31,14 @@ struct MmaFwdCfg {
   static constexpr bool ELIGIBLE = (L >= 8);
   static constexpr int LP = Geo::LP, LD = Geo::LD, BLK = Geo::BLK;
   static constexpr int VEC = 6 * LP;                          // y_even -> x | y_odd | G x | spare | column buffer (2 LP) of the Cholesky
-  static constexpr int REC = 4 * BLK + VEC;                   // doubles per node
-  static constexpr int W = LP <= 16 ? 8 : (LP <= 24 ? 5 : 6); // warps (= nodes incl. the halo) per CTA
+  static constexpr int REC = 3 * BLK + VEC;                   // doubles per owned node: S0 | S2 | S3 | vectors
+  static constexpr int REC_HALO = 2 * BLK + VEC;              // the halo node never forms F: S0 | S3 | vectors
+  // Warps (= nodes incl. the halo) per CTA, chosen so that TWO CTAs fit on an SM: with a single CTA per SM all warps sit in the same
+  // phase (load, Cholesky, products, store) and the memory pipe idles while the tensor pipe works and vice versa (LP = 32 ran
+  // 2.3x off the sum of its parts); two CTAs start at different times and cover each other's phases.
+  static constexpr int W = LP <= 16 ? 8 : (LP <= 24 ? 5 : 4);
   static constexpr int OWN = W - 1;
-  static constexpr size_t SMEM = (size_t)W * REC * sizeof(double);
+  static constexpr size_t SMEM = (size_t)(OWN * REC + REC_HALO) * sizeof(double);
   static constexpr int MIN_CTAS = (2 * (SMEM + 1024) <= 227 * 1024) ? 2 : 1;
 };
 
@@ -45,14 +49,15 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, OWN = C::OWN, NTL = LP / 8, BS = L * L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* N = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::REC;
-  double* S0 = N;
-  double* S2 = N + BLK;
-  double* S3 = N + 2 * BLK;
-  double* S4 = N + 3 * BLK;
-  double* YE = N + 4 * BLK;
+  const bool is_halo = warp == OWN;
+  double* N = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::REC;       // (the halo record is the last one)
+  double* S0 = N;                                          // R_even -> K -> Ki -> R_odd (staged once Ki has been consumed)
+  double* S2 = N + BLK;                                    // O_right -> F          (owned nodes only)
+  double* S3 = is_halo ? N + BLK : N + 2 * BLK;            // O_left -> G -> B
+  double* YE = is_halo ? N + 2 * BLK : N + 3 * BLK;
   double* YO = YE + LP;
   double* V = YO + LP;
+  double* CB = YE + 4 * LP;                                // column buffer of the Cholesky
 
   const int m = a.m;
   const int E = (m + 1) >> 1, o = m >> 1, gcnt = (m - 1) >> 1;
@@ -87,10 +92,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   else mma_fill_block<LP>(S0, true, lane);
   if (has_left) mma_stage_issue<T, L, LP>(S3, srcL, false, lane, vL);
   else mma_fill_block<LP>(S3, false, lane);
-  if (do_f) {
-    mma_stage_issue<T, L, LP>(S2, gO + (size_t)(2 * e) * BS, false, lane, vO);
-    mma_stage_issue<T, L, LP>(S4, gR + (size_t)(2 * e + 1) * BS, false, lane, vR);
-  }
+  if (do_f) mma_stage_issue<T, L, LP>(S2, gO + (size_t)(2 * e) * BS, false, lane, vO);
   if (lane < LP) {
     YE[lane] = ye_v;
     YO[lane] = yo_v;
@@ -100,17 +102,14 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   __syncwarp();
   if (valid) mma_stage_finish<T, L, LP>(S0, true, lane);
   if (has_left) mma_stage_finish<T, L, LP>(S3, false, lane);
-  if (do_f) {
-    mma_stage_finish<T, L, LP>(S2, false, lane);
-    mma_stage_finish<T, L, LP>(S4, false, lane);
-  }
+  if (do_f) mma_stage_finish<T, L, LP>(S2, false, lane);
   __syncwarp();
 
   // ---------------- K, Ki, x ----------------
   double ld_part = 0.0, mh_part = 0.0;
   {
     double invd[LP];
-    const bool bad = warp_cholesky<LP>(S0, N + 4 * BLK + 4 * LP, invd, lane);
+    const bool bad = warp_cholesky<LP>(S0, CB, invd, lane);
     if (own) {
       if (bad && a.info != nullptr && lane == 0) {
         const long long flat = (long long)b * E + e;
@@ -161,6 +160,9 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
       }
     }
   }
+  // Ki has been consumed (x, F, G): its slot takes R_odd, which arrives while the remaining products run
+  __syncwarp();
+  if (do_f) mma_stage_issue<T, L, LP>(S0, gR + (size_t)(2 * e + 1) * BS, false, lane, vR);
   double ur = 0.0, vr = 0.0;
   if (has_y) {
     if (do_f) ur = warp_matvec<LP, false>(S2, YE, lane);                   // F x
@@ -207,13 +209,20 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
     acc_zero<LP>(acc);
     warp_gemm<LP, false, true, K_FULL, false>(acc, S2, S2, lane);          // A = F F^T, kept in registers
   }
+  if (do_f) {                                         // R_odd has landed in S0
+    cp_async_wait_all();
+    __syncwarp();
+    mma_stage_finish<T, L, LP>(S0, false, lane);
+    __syncwarp();
+  }
   if (warp < OWN) pair_wait(warp + 1);                // B and G x of the right neighbour are visible
 
   // ---------------- R~_e = R_odd - A - B_{e+1},  y~_e = y_odd - F x_e - G_e x_{e+1} ----------------
   if (do_f && a.Rn != nullptr) {
     const bool next_even = (e + 1) < E;
-    const double* Bn = N + C::REC + 2 * BLK;          // S3 of the next warp
-    const double* Vn = N + C::REC + 4 * BLK + 2 * LP; // V of the next warp
+    const bool next_halo = (warp + 1) == OWN;         // the record of the halo warp is laid out S0 | S3 | vectors
+    const double* Bn = N + C::REC + (next_halo ? BLK : 2 * BLK);                  // S3 of the next warp
+    const double* Vn = N + C::REC + (next_halo ? 2 * BLK : 3 * BLK) + 2 * LP;     // V of the next warp
     T* Rn = static_cast<T*>(a.Rn) + ((size_t)b * o + e) * BS;
     const bool vec = is_aligned16(a.Rn);
     const int lr = lane >> 2, lc = lane & 3;
@@ -222,7 +231,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
         const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
-        const double2 ro = *reinterpret_cast<const double2*>(S4 + row * LD + col);
+        const double2 ro = *reinterpret_cast<const double2*>(S0 + row * LD + col);
         double v0 = ro.x - acc[mt][nt][0], v1 = ro.y - acc[mt][nt][1];
         if (next_even) {
           const double2 bn = *reinterpret_cast<const double2*>(Bn + row * LD + col);

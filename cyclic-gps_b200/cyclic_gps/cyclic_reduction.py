@@ -243,10 +243,19 @@ def _decompose_impl(Rs, Os):
     pack = _forward_checked(R, O, None, keep_factors=True)
     ell = R.shape[2]
     z = torch.empty((R.shape[0], 0, ell, ell), dtype=R.dtype, device=dev)
-    c = lambda t: _to_caller(t, batched, caller)
-    Ds = [c(d) for d in pack.D]
-    Fs = [c(f) for k, f in enumerate(pack.F[:-1])]
-    Gs = [c(g) if _engine.counts(pack.ms[k])[2] > 0 else c(z) for k, g in enumerate(pack.G[:-1])]
+    if caller == dev:
+        Dl, Fl, Gl = pack.D, pack.F, pack.G                 # zero-copy views of the packed device buffers
+    else:
+        # a caller on another device (the reference's tests pass CPU tensors): ONE copy per factor family, carved into the
+        # per-level views afterwards, instead of three small copies per level
+        B = R.shape[0]
+        rows = [[_engine.counts(m)[i] for m in pack.ms] for i in range(3)]
+        host = lambda flat, r: _engine._carve(flat.to(caller), r, (ell, ell), B) if flat is not None and flat.numel() else [z.to(caller)] * len(r)
+        Dl, Fl, Gl = host(pack.D_flat, rows[0]), host(pack.F_flat, rows[1]), host(pack.G_flat, rows[2])
+    c = (lambda t: t) if batched else (lambda t: t[0])
+    Ds = [c(d) for d in Dl]
+    Fs = [c(f) for f in Fl[:-1]]
+    Gs = [c(g) if _engine.counts(pack.ms[k])[2] > 0 else c(z.to(caller)) for k, g in enumerate(Gl[:-1])]
     ms = torch.tensor(pack.ms, dtype=torch.int64)
     return CRDecomp(ms, Ds, Fs, Gs, pack=pack, Rs=Rs, Os=Os, batched=batched, caller_device=caller)
 
