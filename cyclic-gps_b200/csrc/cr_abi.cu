@@ -96,7 +96,7 @@ int fuse_start(int n, int L, int tile, bool odd_parity_needed, int parity) {
 
 extern "C" {
 
-int crb200_version(void) { return 100; }
+int crb200_version(void) { return 101; }
 int crb200_max_ell(void) { return 32; }
 int crb200_last_cuda_error(void) { return g_last_cuda_error; }
 long long crb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

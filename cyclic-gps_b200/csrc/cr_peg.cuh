@@ -278,214 +278,316 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
-template <typename CT, int L>
-struct PegBwdConsts {
-  PegConsts<CT, L> f;
-  CT Vre[L * L], Vim[L * L], Wre[L * L], Wim[L * L];       // V and V^{-1}
-  // the divided differences Phi_jk are formed in fp64 whatever CT is: e^{c lam_j} - e^{c lam_k} cancels like 1 / |c (lam_j - lam_k)|,
-  // which for small gaps and close eigenvalues leaves no digits in fp32
-  double lred[L], limd[L];
-  double idre[L * L], idim[L * L], deg[L * L];               // 1 / (lam_j - lam_k) (0 where degenerate), degenerate mask
+// One THREAD per gap forms gA (the cotangent of A = exp(cG)), a warp covers 32 consecutive gaps of one series.  The adjoint of
+// the matrix exponential is NOT taken per gap: with Y_g = V^{-1} gA_g^T V and Phi_jk(d) = (e^{c lam_j} - e^{c lam_k}) / (lam_j - lam_k),
+//   Z_jk = sum_g Y_g[k][j] Phi_jk(d_g) = ( T_j[k][j] - T_k[k][j] ) / (lam_j - lam_k),     T_m = V^{-1} ( sum_g e^{c_g lam_m} gA_g^T ) V,
+// (and sum_g c_g e^{c_g lam_m} gA_g^T for the diagonal / equal eigenvalues), so the kernel only accumulates the 2 ell real
+// weighted sums  S[row] = sum_g E[row][g] gA_g^T  in fp64 (the differences cancel like 1 / |c (lam_j - lam_k)|: fp64 weights,
+// fp64 accumulation, exact fp32 x fp64 products) and the host finishes with ell x ell complex algebra.  Rows of E, in order,
+// for every m < nterms:  Re e_m, c Re e_m, and for a complex eigenvalue (lam_im != 0) also Im e_m, c Im e_m  -- 2 ell rows in all
+// because the caller folds conjugate pairs.
+//
+// Data movement: gR / gO / O tiles arrive by cp.async (coalesced 16-byte chunks) in one padded shared-memory record per gap,
+// [ W = gR_g | H = gO_g | O_g ] (+ [ A ] when A and B do not both fit in registers); U = gR_{g+1} is the W field of the next
+// record (33 records per warp).  B = -O_g and A are register-resident, every other operand streams by rows:
+//   pass 1 (rows r):    X1[r] = (Us[r] - H[r] A^T) B - H[r]                     -> O slot (dead once B is in registers)
+//   pass 2 (rows r):    Y3[r] = Ws[r] + (Ws[r] A^T - H[:,r]^T) B + (A^T X1)[r]   -> COLUMN r of the H slot (that column is dead)
+//   pass 3 (columns j): gA[:,j] = X1[:,j] + B Y3[:,j]                           -> row j of the H slot (= gA^T, entry order of S)
+// Then the warps of the CTA share the accumulation: warp w owns rows [w RPW, (w+1) RPW) of E and walks the gA^T records of
+// all NW tiles (lane = entry), so the fp64 accumulators are RPW x ceil(ell^2 / 32) registers per lane instead of 2 ell x that.
+template <typename T, int L>
+struct PegBwdSizes {
+  static constexpr int BS = L * L;
+  static constexpr bool A_REGS = 2 * BS * (int)sizeof(T) <= 512;            // A and B both register-resident
+  static constexpr int NSLOT = A_REGS ? 3 : 4;
+  static constexpr int RS = record_stride<T>(NSLOT * BS, BS);                // record stride (elements)
+  static constexpr int NE = 2 * L;                                           // rows of E
+  static constexpr size_t consts_bytes = align16(2 * L * sizeof(double) + 2 * (size_t)L * BS * sizeof(T));
+  static constexpr size_t warp_bytes = align16((size_t)33 * RS * sizeof(T));
+  static constexpr size_t e_bytes(int nw) { return (size_t)nw * ((NE + nw - 1) / nw) * 32 * sizeof(double); }   // per tile
+  static constexpr size_t cta_bytes(int nw) { return consts_bytes + nw * (warp_bytes + e_bytes(nw)); }
+  static constexpr int warps_per_sm(int nw) { return (int)((size_t)(227 * 1024) / (cta_bytes(nw) + 1024)) * nw; }
+  static constexpr int pick_nw() {
+    int best = 1;
+    for (int nw = 2; nw <= 4; ++nw)
+      if (cta_bytes(nw) + 1024 <= (size_t)227 * 1024 && warps_per_sm(nw) >= warps_per_sm(best)) best = nw;
+    return best;
+  }
+};
+template <typename T, int L>
+struct PegBwdCfg : PegBwdSizes<T, L> {
+  using Sz = PegBwdSizes<T, L>;
+  static constexpr int NW = Sz::pick_nw();
+  static constexpr int RPW = (Sz::NE + NW - 1) / NW;                         // rows of E per warp
+  static constexpr int SLOTS = (Sz::BS + 31) / 32;
+  static constexpr int CTAS_PER_SM = cmax(1, cmin(8, Sz::warps_per_sm(NW) / NW));
+  static constexpr size_t E_TILE_BYTES = Sz::e_bytes(NW);                    // E rows of one tile
+  static constexpr size_t REC_OFFSET = Sz::consts_bytes + NW * E_TILE_BYTES; // first warp's records
+  static constexpr size_t CTA_BYTES = Sz::cta_bytes(NW);
 };
 
 template <typename T, int L>
-__global__ void __launch_bounds__(kPegThreads) cr_peg_bwd_kernel(const PegBwdArgs a) {
-  using CT = T;
-  constexpr int BS = L * L, NZ = 2 * BS, SLOTS = (NZ + 31) / 32;
+struct PegBwdConsts {
+  double lre[L], lim[L];
+  T Mre[L][L * L], Mim[L][L * L];
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel(const PegBwdArgs a) {
+  using Cfg = PegBwdCfg<T, L>;
+  constexpr int BS = Cfg::BS, RS = Cfg::RS, NW = Cfg::NW, RPW = Cfg::RPW, NE = Cfg::NE, SLOTS = Cfg::SLOTS;
+  constexpr bool A_REGS = Cfg::A_REGS;
+  constexpr int AL = A_REGS ? L : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PegBwdConsts<CT, L>* S = reinterpret_cast<PegBwdConsts<CT, L>*>(smem_raw);
-  peg_load_consts<CT, L>(&S->f, a.lam_re, a.lam_im, a.M_re, a.M_im, nullptr);
-  for (int i = threadIdx.x; i < BS; i += blockDim.x) {
-    S->Vre[i] = (CT)a.V_re[i]; S->Vim[i] = (CT)a.V_im[i];
-    S->Wre[i] = (CT)a.Vinv_re[i]; S->Wim[i] = (CT)a.Vinv_im[i];
-    S->idre[i] = a.invdl_re[i]; S->idim[i] = a.invdl_im[i]; S->deg[i] = a.degenerate[i];
-  }
-  for (int i = threadIdx.x; i < L; i += blockDim.x) { S->lred[i] = a.lamfull_re[i]; S->limd[i] = a.lamfull_im[i]; }
-  __syncthreads();
+  PegBwdConsts<T, L>* S = reinterpret_cast<PegBwdConsts<T, L>*>(smem_raw);
+  double* sE = reinterpret_cast<double*>(smem_raw + Cfg::consts_bytes);                       // [NW tiles][NW * RPW rows][32 gaps]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = a.n;
-  const int ngap = n - 1;
+  T* wrec = reinterpret_cast<T*>(smem_raw + Cfg::REC_OFFSET + (size_t)warp * Cfg::warp_bytes);
+  const int nterms = a.nterms > 0 ? a.nterms : L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) { S->lre[i] = a.lam_re[i]; S->lim[i] = a.lam_im[i]; }
+  for (int i = threadIdx.x; i < L * BS; i += blockDim.x) {
+    (&S->Mre[0][0])[i] = (T)a.M_re[i];
+    (&S->Mim[0][0])[i] = (T)a.M_im[i];
+  }
+  for (int i = threadIdx.x; i < NW * NW * RPW * 32; i += blockDim.x) sE[i] = 0.0;              // rows past NE stay zero
+  __syncthreads();
+
+  const int n = a.n, ngap = n - 1;
   const long long tiles_per_series = (ngap + 31) / 32;
   const long long ntiles = tiles_per_series * a.batch;
-  const long long nwarps = (long long)gridDim.x * (kPegThreads / 32);
-  double accZ[SLOTS];
-#pragma unroll
-  for (int i = 0; i < SLOTS; ++i) accZ[i] = 0.0;
-  // per-thread record [ A | B ] behind the constants; the stride keeps the threads of a warp on different banks
-  constexpr int RS = record_stride<CT>(2 * BS, BS);
-  CT* sA = reinterpret_cast<CT*>(smem_raw + align16(sizeof(PegBwdConsts<CT, L>))) + (size_t)threadIdx.x * RS;
-  CT* sB = sA + BS;
-  const int ncols = a.nterms > 0 ? a.nterms : L;     // columns j of Z the kernel produces (the caller mirrors the conjugate ones)
+  const long long stride_tiles = (long long)gridDim.x * NW;
+  const unsigned nsb = (unsigned)(RS * sizeof(T));
+  const unsigned srec0 = smem_u32(wrec);
+  T* rec = wrec + (size_t)lane * RS;                      // this gap's record
+  T* sW = rec;
+  T* sH = rec + BS;
+  T* sX = rec + 2 * BS;                                   // O_g, then X1
+  T* sA = rec + (A_REGS ? 0 : 3 * BS);                    // only used when !A_REGS
+  const T* sU = rec + RS;                                 // W field of the next record = gR_{g+1}
+  double* myE = sE + (size_t)warp * (NW * RPW * 32) + lane;
 
-  for (long long vt = (long long)blockIdx.x * (kPegThreads / 32) + warp; vt < ntiles; vt += nwarps) {
+  double acc[RPW][SLOTS];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) acc[i][s] = 0.0;
+
+  // stage the W (33 rows of gR) and O fields, or the H field, of tile vt
+  auto stage_WO = [&](long long vt) {
     const int b = (int)(vt / tiles_per_series);
-    const int g = (int)(vt - (long long)b * tiles_per_series) * 32 + lane;
-    const bool real = g < ngap;
-    CT gA[L][L];
-    CT c = CT(0);
-#pragma unroll
-    for (int r = 0; r < L; ++r)
-#pragma unroll
-      for (int q = 0; q < L; ++q) gA[r][q] = CT(0);
-    if (real) {
-      const T* gR = static_cast<const T*>(a.gR) + (size_t)b * a.stride_gR;
-      const T* gO = static_cast<const T*>(a.gO) + (size_t)b * a.stride_gO;
-      const T* Og = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
-      const T* Ug = gR + (size_t)(g + 1) * BS;       // U = gR_{g+1}
-      const T* Wg = gR + (size_t)g * BS;             // W = gR_g
-      const T* Hg = gO + (size_t)g * BS;             // H = gO_g
-      const bool vR = is_aligned16(gR), vH = is_aligned16(gO);
-      c = CT(-0.5) * (CT) static_cast<const T*>(a.gaps)[(size_t)b * a.stride_gaps + g];
-      // A and B = -O_g live in this thread's shared-memory record (rows are re-read many times; registers hold X1 and Y3)
+    const int g0 = (int)(vt - (long long)b * tiles_per_series) * 32;
+    const T* gR = static_cast<const T*>(a.gR) + (size_t)b * a.stride_gR + (size_t)g0 * BS;
+    const T* Og = static_cast<const T*>(a.O) + (size_t)b * a.strideO + (size_t)g0 * BS;
+    rec_g2s<T, BS, 1>(srec0, nsb, gR, 0, cmin(33, n - g0), is_aligned16(gR));
+    rec_g2s<T, BS, 1>(srec0 + 2 * BS * (unsigned)sizeof(T), nsb, Og, 0, cmin(32, ngap - g0), is_aligned16(Og));
+  };
+  auto stage_H = [&](long long vt) {
+    const int b = (int)(vt / tiles_per_series);
+    const int g0 = (int)(vt - (long long)b * tiles_per_series) * 32;
+    const T* gO = static_cast<const T*>(a.gO) + (size_t)b * a.stride_gO + (size_t)g0 * BS;
+    rec_g2s<T, BS, 1>(srec0 + BS * (unsigned)sizeof(T), nsb, gO, 0, cmin(32, ngap - g0), is_aligned16(gO));
+  };
+
+  const long long base0 = (long long)blockIdx.x * NW;
+  if (base0 + warp < ntiles) { stage_WO(base0 + warp); stage_H(base0 + warp); }
+  cp_async_commit();
+
+  for (long long base = base0; base < ntiles; base += stride_tiles) {
+    const long long vt = base + warp;
+    const bool tile_ok = vt < ntiles;
+    int g = 0;
+    bool real = false;
+    T Ar[AL][AL], Bm[L][L];
+    double cd = 0.0;
+    if (tile_ok) {
+      const int b = (int)(vt / tiles_per_series);
+      g = (int)(vt - (long long)b * tiles_per_series) * 32 + lane;
+      real = g < ngap;
+      // weights of E and the coefficients of A = I + Re sum_m (e_m - 1) M_m, from fp64 exponentials (the staged tile lands meanwhile)
+      T cre[L], cim[L];
+      if (real) cd = (double)(T(-0.5) * static_cast<const T*>(a.gaps)[(size_t)b * a.stride_gaps + g]);
       {
-        CT A[L][L];
-        peg_expm_minus_I<CT, L>(A, &S->f, c, a.nterms > 0 ? a.nterms : L);
-#pragma unroll
-        for (int r = 0; r < L; ++r) {
-          A[r][r] += CT(1);
-          sts_row<CT, L>(sA + r * L, A[r]);
-        }
-        peg_load_block<T, L>(A, Og + (size_t)g * BS, is_aligned16(Og));
-#pragma unroll
-        for (int r = 0; r < L; ++r) {
-#pragma unroll
-          for (int q = 0; q < L; ++q) A[r][q] = -A[r][q];
-          sts_row<CT, L>(sB + r * L, A[r]);
-        }
-      }
-      CT Y3[L][L];
-      // X1 = (Us - H A^T) B - H,  Us = U + U^T   (rows of U, H stream from global memory / L1; gA holds X1)
-#pragma unroll
-      for (int r = 0; r < L; ++r) {
-        CT hrow[L], us[L], tt[L];
-        peg_load_row<T, L>(hrow, Hg + r * L, vH);
-        peg_load_row<T, L>(us, Ug + r * L, vR);
-#pragma unroll
-        for (int q = 0; q < L; ++q) us[q] += __ldg(Ug + q * L + r);
-#pragma unroll
-        for (int q = 0; q < L; ++q) {
-          CT arow[L];
-          lds_row<CT, L>(arow, sA + q * L);
-          CT sacc = us[q];
-#pragma unroll
-          for (int k = 0; k < L; ++k) sacc = fma(-hrow[k], arow[k], sacc);
-          tt[q] = sacc;
-        }
-#pragma unroll
-        for (int j = 0; j < L; ++j) gA[r][j] = -hrow[j];
-#pragma unroll
-        for (int q = 0; q < L; ++q) {
-          CT brow[L];
-          lds_row<CT, L>(brow, sB + q * L);
-#pragma unroll
-          for (int j = 0; j < L; ++j) gA[r][j] = fma(tt[q], brow[j], gA[r][j]);
-        }
-      }
-      // Y3 = X2 + A^T X1,  X2 = Ws + (Ws A^T - H^T) B,  Ws = W + W^T
-#pragma unroll
-      for (int r = 0; r < L; ++r) {
-        CT ws[L], tt[L];
-        peg_load_row<T, L>(ws, Wg + r * L, vR);
-#pragma unroll
-        for (int q = 0; q < L; ++q) ws[q] += __ldg(Wg + q * L + r);
-#pragma unroll
-        for (int q = 0; q < L; ++q) {
-          CT arow[L];
-          lds_row<CT, L>(arow, sA + q * L);
-          CT sacc = -(CT)__ldg(Hg + q * L + r);
-#pragma unroll
-          for (int k = 0; k < L; ++k) sacc = fma(ws[k], arow[k], sacc);
-          tt[q] = sacc;
-        }
-#pragma unroll
-        for (int j = 0; j < L; ++j) Y3[r][j] = ws[j];
-#pragma unroll
-        for (int q = 0; q < L; ++q) {
-          CT brow[L];
-          lds_row<CT, L>(brow, sB + q * L);
-#pragma unroll
-          for (int j = 0; j < L; ++j) Y3[r][j] = fma(tt[q], brow[j], Y3[r][j]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        CT arow[L];
-        lds_row<CT, L>(arow, sA + k * L);
-#pragma unroll
-        for (int r = 0; r < L; ++r)
-#pragma unroll
-          for (int j = 0; j < L; ++j) Y3[r][j] = fma(arow[r], gA[k][j], Y3[r][j]);
-      }
-      // gA = X1 + B Y3   (in place, row by row)
-#pragma unroll
-      for (int r = 0; r < L; ++r) {
-        CT brow[L];
-        lds_row<CT, L>(brow, sB + r * L);
-#pragma unroll
-        for (int j = 0; j < L; ++j) {
-          CT sacc = gA[r][j];
-#pragma unroll
-          for (int k = 0; k < L; ++k) sacc = fma(brow[k], Y3[k][j], sacc);
-          gA[r][j] = sacc;
-        }
-      }
-    }
-    // Daleckii-Krein in the eigenbasis: T = gA^T V (column j), Y_kj = sum_m Vinv[k][m] T[m][j], Z_jk = Y_kj Phi_jk
-    double ere[L], eim[L];                                         // e^{c lam_k} in fp64 (see PegBwdConsts)
-    const double cd = (double)c;
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-      const double ea = exp(cd * S->lred[k]);
-      double sb, cb;
-      sincos(cd * S->limd[k], &sb, &cb);
-      ere[k] = ea * cb;
-      eim[k] = ea * sb;
-    }
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-      if (j >= ncols) break;                                         // uniform
-      CT Tre[L], Tim[L];
-#pragma unroll
-      for (int m = 0; m < L; ++m) {
-        CT sr = CT(0), si = CT(0);
-#pragma unroll
-        for (int p = 0; p < L; ++p) {
-          sr = fma(gA[p][m], S->Vre[p * L + j], sr);
-          si = fma(gA[p][m], S->Vim[p * L + j], si);
-        }
-        Tre[m] = sr; Tim[m] = si;
-      }
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        CT yr = CT(0), yi = CT(0);
+        int row = 0;
 #pragma unroll
         for (int m = 0; m < L; ++m) {
-          const CT wr = S->Wre[k * L + m], wi = S->Wim[k * L + m];
-          yr = fma(wr, Tre[m], fma(-wi, Tim[m], yr));
-          yi = fma(wr, Tim[m], fma(wi, Tre[m], yi));
+          if (m >= nterms) break;                                     // uniform
+          const bool cplx = S->lim[m] != 0.0;                         // uniform
+          if (row + (cplx ? 4 : 2) > NE) break;                       // conjugate pairs not folded by the caller: rows beyond 2 ell are dropped
+          const double ea = exp(cd * S->lre[m]);
+          double sb = 0.0, cb = 1.0;
+          if (cplx) sincos(cd * S->lim[m], &sb, &cb);
+          const double er = ea * cb, ei = ea * sb;
+          cre[m] = (T)(er - 1.0);
+          cim[m] = (T)ei;
+          const double w = real ? 1.0 : 0.0;
+          myE[(row + 0) * 32] = w * er;
+          myE[(row + 1) * 32] = w * cd * er;
+          row += 2;
+          if (cplx) {
+            myE[(row + 0) * 32] = w * ei;
+            myE[(row + 1) * 32] = w * cd * ei;
+            row += 2;
+          }
         }
-        // Phi_jk = (e_j - e_k) / (lam_j - lam_k), or c e_j where the eigenvalues coincide
-        const double dr = ere[j] - ere[k], di = eim[j] - eim[k];
-        const double ir = S->idre[j * L + k], ii = S->idim[j * L + k], dg = S->deg[j * L + k] * cd;
-        const CT pr = (CT)(dr * ir - di * ii + dg * ere[j]);
-        const CT pi = (CT)(dr * ii + di * ir + dg * eim[j]);
-        CT zr = yr * pr - yi * pi, zi = yr * pi + yi * pr;          // butterfly over the 32 gaps of the tile in CT,
+      }
+      if (real) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {                      // accumulation across tiles in fp64
-          zr += __shfl_xor_sync(0xffffffffu, zr, off);
-          zi += __shfl_xor_sync(0xffffffffu, zi, off);
+        for (int r = 0; r < L; ++r) {
+          T arow[L];
+#pragma unroll
+          for (int q = 0; q < L; ++q) arow[q] = (r == q) ? T(1) : T(0);
+#pragma unroll
+          for (int m = 0; m < L; ++m) {
+            if (m >= nterms) break;                                   // uniform
+#pragma unroll
+            for (int q = 0; q < L; ++q) arow[q] = fma(cre[m], S->Mre[m][r * L + q], fma(-cim[m], S->Mim[m][r * L + q], arow[q]));
+          }
+          if constexpr (A_REGS) {
+#pragma unroll
+            for (int q = 0; q < L; ++q) Ar[r][q] = arow[q];
+          } else {
+            sts_row<T, L>(sA + r * L, arow);
+          }
         }
-        const int s0 = 2 * (j * L + k), s1 = s0 + 1;
-        if (lane == (s0 & 31)) accZ[s0 >> 5] += (double)zr;
-        if (lane == (s1 & 31)) accZ[s1 >> 5] += (double)zi;
       }
     }
-  }
-  // one atomic per entry and warp: entry s lives on lane s % 32, slot s / 32
+    cp_async_wait_all();
+    __syncwarp();
+    if (tile_ok) {
+      if (real) {
 #pragma unroll
-  for (int i = 0; i < SLOTS; ++i) {
-    const int s = i * 32 + lane;
-    if (s < NZ) atomicAdd(a.Z + s, accZ[i]);
+        for (int r = 0; r < L; ++r) {
+          lds_row<T, L>(Bm[r], sX + r * L);
+#pragma unroll
+          for (int q = 0; q < L; ++q) Bm[r][q] = -Bm[r][q];
+        }
+        // pass 1: X1 rows -> O slot
+#pragma unroll
+        for (int r = 0; r < L; ++r) {
+          T hrow[L], us[L], t1[L], x[L];
+          lds_row<T, L>(hrow, sH + r * L);
+          lds_row<T, L>(us, sU + r * L);
+#pragma unroll
+          for (int q = 0; q < L; ++q) us[q] += sU[q * L + r];
+#pragma unroll
+          for (int q = 0; q < L; ++q) {
+            T arow[L];
+            if constexpr (A_REGS) {
+#pragma unroll
+              for (int k = 0; k < L; ++k) arow[k] = Ar[q % AL][k % AL];
+            } else {
+              lds_row<T, L>(arow, sA + q * L);
+            }
+            T sacc = us[q];
+#pragma unroll
+            for (int k = 0; k < L; ++k) sacc = fma(-hrow[k], arow[k], sacc);
+            t1[q] = sacc;
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j) x[j] = -hrow[j];
+#pragma unroll
+          for (int q = 0; q < L; ++q)
+#pragma unroll
+            for (int j = 0; j < L; ++j) x[j] = fma(t1[q], Bm[q][j], x[j]);
+          sts_row<T, L>(sX + r * L, x);
+          sched_fence();
+        }
+        // pass 2: Y3 rows -> columns of the H slot
+#pragma unroll
+        for (int r = 0; r < L; ++r) {
+          T ws[L], t2[L], y[L];
+          lds_row<T, L>(ws, sW + r * L);
+#pragma unroll
+          for (int q = 0; q < L; ++q) ws[q] += sW[q * L + r];
+#pragma unroll
+          for (int q = 0; q < L; ++q) {
+            T arow[L];
+            if constexpr (A_REGS) {
+#pragma unroll
+              for (int k = 0; k < L; ++k) arow[k] = Ar[q % AL][k % AL];
+            } else {
+              lds_row<T, L>(arow, sA + q * L);
+            }
+            T sacc = -sH[q * L + r];
+#pragma unroll
+            for (int k = 0; k < L; ++k) sacc = fma(ws[k], arow[k], sacc);
+            t2[q] = sacc;
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j) y[j] = ws[j];
+#pragma unroll
+          for (int q = 0; q < L; ++q)
+#pragma unroll
+            for (int j = 0; j < L; ++j) y[j] = fma(t2[q], Bm[q][j], y[j]);
+#pragma unroll
+          for (int k = 0; k < L; ++k) {
+            T xr[L];
+            lds_row<T, L>(xr, sX + k * L);
+            T akr;
+            if constexpr (A_REGS) akr = Ar[k % AL][r % AL]; else akr = sA[k * L + r];
+#pragma unroll
+            for (int j = 0; j < L; ++j) y[j] = fma(akr, xr[j], y[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j) sH[j * L + r] = y[j];
+          sched_fence();
+        }
+        // pass 3: gA columns -> rows of the H slot (gA^T)
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          T yc[L], ga[L];
+          lds_row<T, L>(yc, sH + j * L);
+#pragma unroll
+          for (int r = 0; r < L; ++r) ga[r] = sX[r * L + j];
+#pragma unroll
+          for (int r = 0; r < L; ++r)
+#pragma unroll
+            for (int k = 0; k < L; ++k) ga[r] = fma(Bm[r][k], yc[k], ga[r]);
+          sts_row<T, L>(sH + j * L, ga);
+          sched_fence();
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) sH[i] = T(0);                    // no gap here: contributes nothing (and no NaN x 0)
+      }
+    }
+    __syncwarp();
+    const long long next = vt + stride_tiles;
+    if (next < ntiles) stage_WO(next);                                // W and X1 are dead for every lane of this warp
+    __syncthreads();
+    // accumulation: this warp's rows of E against the gA^T records of every tile of the CTA
+#pragma unroll 1
+    for (int tt = 0; tt < NW; ++tt) {
+      if (base + tt >= ntiles) break;                                 // uniform
+      const double* Et = sE + (size_t)tt * (NW * RPW * 32) + (size_t)warp * RPW * 32;
+      const T* grec = reinterpret_cast<const T*>(smem_raw + Cfg::REC_OFFSET + (size_t)tt * Cfg::warp_bytes) + BS;
+#pragma unroll 4
+      for (int gg = 0; gg < 32; ++gg) {
+        double e[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) e[i] = Et[i * 32 + gg];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const int entry = lane + 32 * s;
+          const double v = (entry < BS) ? (double)grec[(size_t)gg * RS + entry] : 0.0;
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) acc[i][s] = fma(e[i], v, acc[i][s]);
+        }
+      }
+    }
+    __syncthreads();
+    if (next < ntiles) stage_H(next);
+    cp_async_commit();
+  }
+  cp_async_wait_all();
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int row = warp * RPW + i;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int entry = lane + 32 * s;
+      if (row < NE && entry < BS) atomicAdd(a.S + (size_t)row * BS + entry, acc[i][s]);
+    }
   }
 }
 
@@ -504,17 +606,20 @@ cudaError_t launch_peg_fwd(const PegFwdArgs& a, cudaStream_t stream) {
 
 template <typename T, int L>
 cudaError_t launch_peg_bwd(const PegBwdArgs& a, cudaStream_t stream) {
-  const size_t smem = align16(sizeof(PegBwdConsts<T, L>)) + (size_t)kPegThreads * record_stride<T>(2 * L * L, L * L) * sizeof(T);
+  using Cfg = PegBwdCfg<T, L>;
+  const size_t smem = Cfg::CTA_BYTES;
   static std::atomic<unsigned char> attr_done[kMaxDevices];
   if (cudaError_t e = ensure_dynamic_smem(cr_peg_bwd_kernel<T, L>, (int)smem, attr_done); e != cudaSuccess) return e;
   if (a.n < 2 || a.batch <= 0) return cudaSuccess;
   const long long tiles = (long long)((a.n - 1 + 31) / 32) * a.batch;
-  int dev = 0, sms = 148;
+  int dev = 0, sms = 148, resident = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long grid = (tiles + kPegThreads / 32 - 1) / (kPegThreads / 32);
-  const long long cap = (long long)sms * 8;                      // persistent warps: at most 8 CTAs per SM worth of blocks
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cr_peg_bwd_kernel<T, L>, Cfg::NW * 32, smem) != cudaSuccess || resident < 1)
+    resident = Cfg::CTAS_PER_SM;
+  long long grid = (tiles + Cfg::NW - 1) / Cfg::NW;
+  const long long cap = (long long)sms * resident;               // persistent CTAs: exactly one resident wave
   if (grid > cap) grid = cap;
-  cr_peg_bwd_kernel<T, L><<<(unsigned)grid, kPegThreads, smem, stream>>>(a);
+  cr_peg_bwd_kernel<T, L><<<(unsigned)grid, Cfg::NW * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

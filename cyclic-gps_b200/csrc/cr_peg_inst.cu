@@ -47,10 +47,9 @@ int crb200_peg_precision_fwd(int dtype, int ell, const crb200_peg_fwd_args* a, v
 int crb200_peg_precision_bwd(int dtype, int ell, const crb200_peg_bwd_args* a, void* stream) {
   if (a == nullptr) return CRB200_EINVAL;
   if ((dtype != CRB200_F32 && dtype != CRB200_F64) || ell < 1 || ell > crb200::kPegMaxEll) return CRB200_EUNSUPPORTED;
-  if (a->batch < 0 || a->n < 1 || a->Z == nullptr || a->lam_re == nullptr || a->lam_im == nullptr || a->M_re == nullptr || a->M_im == nullptr ||
-      a->V_re == nullptr || a->V_im == nullptr || a->Vinv_re == nullptr || a->Vinv_im == nullptr || a->invdl_re == nullptr ||
-      a->invdl_im == nullptr || a->degenerate == nullptr || a->lamfull_re == nullptr || a->lamfull_im == nullptr)
+  if (a->batch < 0 || a->n < 1 || a->S == nullptr || a->lam_re == nullptr || a->lam_im == nullptr || a->M_re == nullptr || a->M_im == nullptr)
     return CRB200_EINVAL;
+  if (a->nterms < 0 || a->nterms > ell) return CRB200_EINVAL;
   if (a->n > 1 && (a->O == nullptr || a->gaps == nullptr || a->gR == nullptr || a->gO == nullptr)) return CRB200_EINVAL;
   if (a->batch == 0 || a->n < 2) return CRB200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -91,10 +91,8 @@ class PegFwdArgs(C.Structure):
 class PegBwdArgs(C.Structure):
     _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
                 ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp),
-                ("V_re", _vp), ("V_im", _vp), ("Vinv_re", _vp), ("Vinv_im", _vp),
-                ("invdl_re", _vp), ("invdl_im", _vp), ("degenerate", _vp),
-                ("O", _vp), ("strideO", _ll), ("gR", _vp), ("gO", _vp), ("stride_gR", _ll), ("stride_gO", _ll), ("Z", _vp),
-                ("nterms", _i), ("lamfull_re", _vp), ("lamfull_im", _vp)]
+                ("O", _vp), ("strideO", _ll), ("gR", _vp), ("gO", _vp), ("stride_gR", _ll), ("stride_gO", _ll), ("S", _vp),
+                ("nterms", _i)]
 
 
 EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",

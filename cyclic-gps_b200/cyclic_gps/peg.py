@@ -70,17 +70,43 @@ class _EigConsts:
         dl = lam.unsqueeze(1) - lam.unsqueeze(0)
         deg = dl.abs() <= 1e-9 * lam.abs().max().clamp_min(1e-300)
         invdl = torch.where(deg, torch.zeros_like(dl), 1.0 / torch.where(deg, torch.ones_like(dl), dl))
-        parts = [lam_t.real, lam_t.imag, M_t.real, M_t.imag, V.real, V.imag, Vinv.real, Vinv.imag, invdl.real, invdl.imag, deg.to(torch.float64),
-                 lam.real, lam.imag]
+        parts = [lam_t.real, lam_t.imag, M_t.real, M_t.imag]
         flat = torch.cat([p.reshape(-1).to(torch.float64) for p in parts]).contiguous()
         self.buf = flat.to(dev)
-        self.V, self.Vinv = V.to(dev), Vinv.to(dev)
         base, off, ptrs = self.buf.data_ptr(), 0, []
         for p in parts:
             ptrs.append(base + 8 * off)
             off += p.numel()
-        (self.lam_re, self.lam_im, self.M_re, self.M_im, self.V_re, self.V_im, self.Vinv_re, self.Vinv_im,
-         self.invdl_re, self.invdl_im, self.deg, self.lamfull_re, self.lamfull_im) = ptrs
+        self.lam_re, self.lam_im, self.M_re, self.M_im = ptrs
+        # host side of the backward pass (finish_expm_adjoint): which rows of the kernel's S belong to which eigenvalue
+        rows, r = [], 0
+        for m in range(nt):
+            cplx = float(lam_t[m].imag) != 0.0
+            rows.append((r, r + 1, r + 2 if cplx else -1, r + 3 if cplx else -1))
+            r += 4 if cplx else 2
+        self.folded = self.partner is not None and r == 2 * l
+        self.rows = rows
+        self.V, self.Vinv = V.to(dev), Vinv.to(dev)
+        self.invdl, self.deg = invdl.to(dev), deg.to(dev)
+
+    def finish_expm_adjoint(self, S):
+        """S (2l, l, l) from crb200_peg_precision_bwd -> gG (l, l) real.  T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V for all l
+        eigenvalues (conjugates by conjugation), Z_jk = (T_j - T_k)[k, j] / (lam_j - lam_k), the c-weighted sums on the
+        diagonal and for equal eigenvalues, gG = Re(V^{-T} Z V^T) (Daleckii-Krein)."""
+        l = self.V.shape[0]
+        Sc = torch.zeros((2, l, l, l), dtype=torch.complex128, device=S.device)       # [plain | c-weighted][m]
+        for m, (r0, r1, i0, i1) in enumerate(self.rows):
+            Sc[0, m] = torch.complex(S[r0], S[i0] if i0 >= 0 else torch.zeros_like(S[r0]))
+            Sc[1, m] = torch.complex(S[r1], S[i1] if i1 >= 0 else torch.zeros_like(S[r1]))
+        for m in range(self.nterms, l):
+            Sc[:, m] = Sc[:, self.partner[m]].conj()
+        Tm = self.Vinv @ Sc @ self.V                                                  # (2, m, k, j)
+        idx = torch.arange(l, device=S.device)
+        Tj = Tm[0][idx, :, idx]                                                       # [j, k] = T_j[k, j]
+        Tk = torch.einsum("kkj->jk", Tm[0])                                           # [j, k] = T_k[k, j]
+        Tc = Tm[1][idx, :, idx]                                                       # [j, k] = T'_j[k, j]
+        Z = (Tj - Tk) * self.invdl + torch.where(self.deg, Tc, torch.zeros_like(Tc))
+        return (self.Vinv.transpose(0, 1) @ Z @ self.V.transpose(0, 1)).real
 
 
 class _PegFn(torch.autograd.Function):
@@ -111,23 +137,15 @@ class _PegFn(torch.autograd.Function):
         dev = gaps.device
         gG = gshift = None
         if ctx.needs_input_grad[1]:
-            Z = torch.zeros(2 * l * l, dtype=torch.float64, device=dev)
+            S = torch.zeros((2 * l, l, l), dtype=torch.float64, device=dev)
             if n > 1:
                 gRc = _engine._rows_contiguous(gR.to(dtype))
                 gOc = _engine._rows_contiguous(gO.to(dtype))
                 _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
-                                lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im, V_re=c.V_re, V_im=c.V_im,
-                                Vinv_re=c.Vinv_re, Vinv_im=c.Vinv_im, invdl_re=c.invdl_re, invdl_im=c.invdl_im, degenerate=c.deg,
-                                O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), Z=Z,
-                                nterms=c.nterms, lamfull_re=c.lamfull_re, lamfull_im=c.lamfull_im)
-            Zc = torch.view_as_complex(Z.view(l, l, 2))
-            if c.partner is not None and c.nterms < l:      # rows the kernel skipped: Z[j', k'] = conj(Z[j, k])
-                part = torch.tensor(c.partner, device=dev)
-                mirrored = Zc[part][:, part].conj()
-                rows = torch.arange(l, device=dev).unsqueeze(1) < c.nterms
-                Zc = torch.where(rows, Zc, mirrored)
-            gG = (c.Vinv.transpose(0, 1) @ Zc @ c.V.transpose(0, 1)).real      # adjoint of expm in the eigenbasis, back in G's basis
-            gG = gG.to(*ctx.G_meta)
+                                lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im,
+                                O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), S=S,
+                                nterms=c.nterms)
+            gG = c.finish_expm_adjoint(S).to(*ctx.G_meta)
         if ctx.shift_meta is not None and ctx.needs_input_grad[2]:
             gshift = gR.sum(dim=(0, 1), dtype=torch.float64).to(*ctx.shift_meta)
         return None, gG, gshift, None
@@ -162,7 +180,7 @@ def peg_precision(gaps, G, shift=None, check=True):
         R, O = peg_precision_torch(g2, Gd, shift.to(g2.device, g2.dtype) if shift is not None else None)
     else:
         consts = _consts_for(G, g2.device)
-        if consts.cond > EIG_COND_MAX:
+        if consts.cond > EIG_COND_MAX or not consts.folded:
             R, O = peg_precision_torch(g2, G.to(g2.device, g2.dtype), shift.to(g2.device, g2.dtype) if shift is not None else None)
         else:
             R, O = _PegFn.apply(g2.contiguous(), G, shift, consts)

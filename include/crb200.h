@@ -161,8 +161,12 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* args, void
  * posterior shift of compute_posterior_precision (:254-268) folded in, and torch autograd through them.  The caller
  * eigendecomposes G = V diag(lam) V^{-1} once on the host (as the reference's compute_eG does, model_utils.py:12-29) and
  * passes lam, M_k = V[:,k] V^{-1}[k,:] (k-major, ell*ell each) as DEVICE arrays of doubles; gaps are d_g = t_{g+1} - t_g > 0.
- * Forward writes R (batch,n,l,l) and O (batch,n-1,l,l).  Backward turns cotangents gR / gO into Z (2*l*l doubles, re/im
- * interleaved, ACCUMULATED into -- zero it first), from which gG = Re(V^{-T} Z V^T); the cotangent of `shift` is sum_i gR_i.
+ * Forward writes R (batch,n,l,l) and O (batch,n-1,l,l).  Backward turns cotangents gR / gO into the cotangent gA_g of every
+ * A_g = exp(c_g G), c_g = -d_g / 2, and returns the 2*l weighted sums  S[row] = sum_g E[row][g] gA_g^T  (l x l each, fp64,
+ * ACCUMULATED into -- zero S first).  Rows, in order, for every m < nterms: Re e^{c lam_m}, c Re e^{c lam_m}, and if lam_im[m] != 0
+ * also Im e^{c lam_m}, c Im e^{c lam_m} (conjugate pairs folded: always 2*l rows).  The caller finishes the adjoint of the matrix
+ * exponential: T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V, Z_jk = (T_j - T_k)[k][j] / (lam_j - lam_k) (the c-weighted sum where the
+ * eigenvalues coincide), gG = Re(V^{-T} Z V^T); the cotangent of `shift` is sum_i gR_i.
  * info (may be NULL): set to 1 if some I - A A^T was not positive definite (a non-positive gap). */
 typedef struct crb200_peg_fwd_args {
   int batch, n;
@@ -180,15 +184,11 @@ typedef struct crb200_peg_fwd_args {
 typedef struct crb200_peg_bwd_args {
   int batch, n;
   const void* gaps; long long stride_gaps;
-  const double* lam_re; const double* lam_im; const double* M_re; const double* M_im;
-  const double* V_re; const double* V_im; const double* Vinv_re; const double* Vinv_im;   /* (l,l) row-major */
-  const double* invdl_re; const double* invdl_im;      /* 1 / (lam_j - lam_k), 0 where the pair is treated as degenerate */
-  const double* degenerate;                            /* 1.0 on the diagonal and for (numerically) equal eigenvalues, else 0.0 */
+  const double* lam_re; const double* lam_im; const double* M_re; const double* M_im;   /* as in crb200_peg_fwd_args */
   const void* O; long long strideO;                    /* the forward result */
   const void* gR; const void* gO; long long stride_gR, stride_gO;
-  double* Z;
-  int nterms;                                          /* as in crb200_peg_fwd_args, for lam / M (the V, Vinv, invdl arrays are always full) */
-  const double* lamfull_re; const double* lamfull_im;  /* all ell eigenvalues, in the order of V's columns */
+  double* S;                                           /* (2*ell, ell*ell) doubles, ACCUMULATED into: see above */
+  int nterms;                                          /* as in crb200_peg_fwd_args */
 } crb200_peg_bwd_args;
 
 int crb200_peg_precision_fwd(int dtype, int ell, const crb200_peg_fwd_args* args, void* stream);
