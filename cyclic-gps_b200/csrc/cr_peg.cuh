@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
 #pragma unroll
     for (int q = 0; q <= r; ++q) Pm1[r][q] = Qm1[r][q] = CT(0);
   bool bad = false;
+  double ld = 0.0;                            // -logdet(I - A A^T) of this gap (lanes >= 1: the gap belongs to this tile)
   if (real) {
     const CT c = CT(-0.5) * (CT)gaps[g];
     CT D[L][L];
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
         K[r][q] = -s;
       }
     CT inv[L];
+    double kprod = 1.0;
 #pragma unroll
     for (int k = 0; k < L; ++k) {
       const CT d = K[k][k];
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
       const CT lkk = sqrt(d);
       inv[k] = CT(1) / lkk;
       K[k][k] = lkk;
+      kprod *= (double)lkk;
 #pragma unroll
       for (int r = k + 1; r < L; ++r) K[r][k] *= inv[k];
 #pragma unroll
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
 #pragma unroll
         for (int r = q; r < L; ++r) K[r][q] = fma(-K[r][k], K[q][k], K[r][q]);
     }
+    if (a.logdet != nullptr && lane >= 1) ld = -2.0 * log(kprod);
     // A = I + D;  B = (K K^T)^{-1} A by two triangular solves per column block (rows of the solve are independent columns)
     CT Bm[L][L];
 #pragma unroll
@@ -259,6 +263,11 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
     }
   }
   if (bad && a.info != nullptr) atomicMax(a.info, 1);
+  if (a.logdet != nullptr) {                  // logdet of the whole block-tridiagonal precision = -sum_g logdet(I - A_g A_g^T)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
+    if (lane == 0 && ld != 0.0) atomicAdd(a.logdet + b, ld);
+  }
   // row r = g (lanes 1..31): R_r = I + (P_{g-1} - I) + (Q_g - I) + shift
   CT Rr[L][L];
 #pragma unroll
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
 // record (33 records per warp).  B = -O_g and A are register-resident, every other operand streams by rows:
 //   pass 1 (rows r):    X1[r] = (Us[r] - H[r] A^T) B - H[r]                     -> O slot (dead once B is in registers)
 //   pass 2 (rows r):    Y3[r] = Ws[r] + (Ws[r] A^T - H[:,r]^T) B + (A^T X1)[r]   -> COLUMN r of the H slot (that column is dead)
-//   pass 3 (columns j): gA[:,j] = X1[:,j] + B Y3[:,j]                           -> row j of the H slot (= gA^T, entry order of S)
+//   pass 3 (columns j): gA[:,j] = X1[:,j] + B Y3[:,j] (+ 2 gld B[:,j])          -> row j of the H slot (= gA^T, entry order of S)
 // Then the warps of the CTA share the accumulation: warp w owns rows [w RPW, (w+1) RPW) of E and walks the gA^T records of
 // all NW tiles (lane = entry), so the fp64 accumulators are RPW x ceil(ell^2 / 32) registers per lane instead of 2 ell x that.
 template <typename T, int L>
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
   constexpr int AL = A_REGS ? L : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PegBwdConsts<T, L>* S = reinterpret_cast<PegBwdConsts<T, L>*>(smem_raw);
-  double* sE = reinterpret_cast<double*>(smem_raw + Cfg::consts_bytes);                       // [NW tiles][NW * RPW rows][32 gaps]
+  double* sE = reinterpret_cast<double*>(smem_raw + Cfg::consts_bytes);                       // [NW tiles][NW row chunks][32 gaps][RPW rows]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* wrec = reinterpret_cast<T*>(smem_raw + Cfg::REC_OFFSET + (size_t)warp * Cfg::warp_bytes);
   const int nterms = a.nterms > 0 ? a.nterms : L;
@@ -364,13 +373,16 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
   T* sX = rec + 2 * BS;                                   // O_g, then X1
   T* sA = rec + (A_REGS ? 0 : 3 * BS);                    // only used when !A_REGS
   const T* sU = rec + RS;                                 // W field of the next record = gR_{g+1}
-  double* myE = sE + (size_t)warp * (NW * RPW * 32) + lane;
+  double* myE = sE + (size_t)warp * (NW * RPW * 32) + (size_t)lane * RPW;       // E of this gap: [row chunk of warp w][gap][RPW rows]
+  auto e_slot = [&](int row) -> double& { return myE[(row / RPW) * (32 * RPW) + (row % RPW)]; };
 
-  double acc[RPW][SLOTS];
+  double acc[RPW][SLOTS], accW[SLOTS];
 #pragma unroll
-  for (int i = 0; i < RPW; ++i)
+  for (int s = 0; s < SLOTS; ++s) {
+    accW[s] = 0.0;
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) acc[i][s] = 0.0;
+    for (int i = 0; i < RPW; ++i) acc[i][s] = 0.0;
+  }
 
   // stage the W (33 rows of gR) and O fields, or the H field, of tile vt
   auto stage_WO = [&](long long vt) {
@@ -399,8 +411,10 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
     bool real = false;
     T Ar[AL][AL], Bm[L][L];
     double cd = 0.0;
+    T gl2 = T(0);                                                     // 2 x cotangent of this series' logdet output
     if (tile_ok) {
       const int b = (int)(vt / tiles_per_series);
+      if (a.g_logdet != nullptr) gl2 = (T)(2.0 * a.g_logdet[b]);
       g = (int)(vt - (long long)b * tiles_per_series) * 32 + lane;
       real = g < ngap;
       // weights of E and the coefficients of A = I + Re sum_m (e_m - 1) M_m, from fp64 exponentials (the staged tile lands meanwhile)
@@ -420,12 +434,12 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
           cre[m] = (T)(er - 1.0);
           cim[m] = (T)ei;
           const double w = real ? 1.0 : 0.0;
-          myE[(row + 0) * 32] = w * er;
-          myE[(row + 1) * 32] = w * cd * er;
+          e_slot(row + 0) = w * er;
+          e_slot(row + 1) = w * cd * er;
           row += 2;
           if (cplx) {
-            myE[(row + 0) * 32] = w * ei;
-            myE[(row + 1) * 32] = w * cd * ei;
+            e_slot(row + 0) = w * ei;
+            e_slot(row + 1) = w * cd * ei;
             row += 2;
           }
         }
@@ -538,7 +552,7 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
           T yc[L], ga[L];
           lds_row<T, L>(yc, sH + j * L);
 #pragma unroll
-          for (int r = 0; r < L; ++r) ga[r] = sX[r * L + j];
+          for (int r = 0; r < L; ++r) ga[r] = fma(gl2, Bm[r][j], sX[r * L + j]);    // d(-logdet(I - A A^T)) / dA = 2 B
 #pragma unroll
           for (int r = 0; r < L; ++r)
 #pragma unroll
@@ -550,6 +564,19 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
 #pragma unroll
         for (int i = 0; i < BS; ++i) sH[i] = T(0);                    // no gap here: contributes nothing (and no NaN x 0)
       }
+    }
+    __syncwarp();
+    if (tile_ok) {
+      // cotangent of `shift` = sum of all gR rows: the rows of this tile (row g0 + 32 is the next tile's first one, unless the series ends here)
+      const int g0 = g - lane;
+      const int cnt = (g0 + 32 >= ngap) ? n - g0 : 32;
+#pragma unroll 4
+      for (int gg = 0; gg < cnt; ++gg)
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const int entry = lane + 32 * s;
+          if (entry < BS) accW[s] += (double)wrec[(size_t)gg * RS + entry];
+        }
     }
     __syncwarp();
     const long long next = vt + stride_tiles;
@@ -564,8 +591,7 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
 #pragma unroll 4
       for (int gg = 0; gg < 32; ++gg) {
         double e[RPW];
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) e[i] = Et[i * 32 + gg];
+        lds_row<double, RPW>(e, Et + gg * RPW);
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
           const int entry = lane + 32 * s;
@@ -588,6 +614,11 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
       const int entry = lane + 32 * s;
       if (row < NE && entry < BS) atomicAdd(a.S + (size_t)row * BS + entry, acc[i][s]);
     }
+  }
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int entry = lane + 32 * s;
+    if (entry < BS) atomicAdd(a.S + (size_t)NE * BS + entry, accW[s]);
   }
 }
 

@@ -85,14 +85,14 @@ _dp = C.POINTER(C.c_double)
 class PegFwdArgs(C.Structure):
     _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
                 ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp), ("shift", _vp),
-                ("R", _vp), ("O", _vp), ("strideR", _ll), ("strideO", _ll), ("info", _vp), ("nterms", _i)]
+                ("R", _vp), ("O", _vp), ("strideR", _ll), ("strideO", _ll), ("info", _vp), ("nterms", _i), ("logdet", _vp)]
 
 
 class PegBwdArgs(C.Structure):
     _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
                 ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp),
                 ("O", _vp), ("strideO", _ll), ("gR", _vp), ("gO", _vp), ("stride_gR", _ll), ("stride_gO", _ll), ("S", _vp),
-                ("nterms", _i)]
+                ("nterms", _i), ("g_logdet", _vp)]
 
 
 EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",

@@ -16,6 +16,10 @@ from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_an
 from cyclic_gps.model_utils import build_2x2_block, build_3x3_block, compute_eG, gaussian_stitch
 from cyclic_gps.peg import peg_precision
 
+# log_likelihood: take log det of the prior precision from the precision builder (one cyclic reduction per evaluation) instead of
+# a second factorisation as the reference does (models.py:349-353).  Same value (an algebraic identity, see peg.peg_precision).
+FUSED_PRIOR_LOGDET = True
+
 try:  # pragma: no cover - not installed in the build image
     import pytorch_lightning as pl
     _Base = pl.LightningModule
@@ -115,13 +119,14 @@ class LEGFamily(_Base):
             return t.device
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _precision_blocks(self, ts, shift=None):
+    def _precision_blocks(self, ts, shift=None, logdet=False):
         """(Rs, Os) on the compute device, built by ONE kernel from the time gaps (cyclic_gps.peg) with a
-        hand-written backward to G and the diagonal shift.  ts (n,) or (B,n)."""
+        hand-written backward to G and the diagonal shift.  ts (n,) or (B,n).  logdet=True: also log det of the unshifted
+        (prior) precision, a by-product of the same kernel."""
         dev = self._compute_device(ts)
         t = ts.to(dev)
         gaps = (t[..., 1:] - t[..., :-1]).to(self.G.dtype)
-        return peg_precision(gaps, self.G, shift)
+        return peg_precision(gaps, self.G, shift, logdet=logdet)
 
     def compute_PEG_precision(self, ts):
         """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision, on the caller's device; a leading
@@ -160,7 +165,8 @@ class LEGFamily(_Base):
         return mean.to(out), {k: v.to(out) for k, v in cov.items()}
 
     def log_likelihood(self, ts, xs):
-        """log p(xs | ts) through two CR factorisations (reference models.py:301-372).  ts (n,), xs (n,d) give a
+        """log p(xs | ts) (reference models.py:301-372: two CR factorisations; here the prior's log-determinant comes out of the
+        precision builder and only the posterior precision is factorised -- FUSED_PRIOR_LOGDET = False restores the two sweeps).  ts (n,), xs (n,d) give a
         scalar as in the reference; a batch of independent series, ts (B,n) and xs (B,n,d), gives (B,) values from
         ONE batched pass of the CR engine (the series share the model parameters).  Only ts and xs travel to the GPU:
         the precision blocks are built there (``_precision_blocks``)."""
@@ -172,9 +178,16 @@ class LEGFamily(_Base):
         obs_mahal = torch.sum(white * xs_d, dim=(-1, -2))
         obs_logdet = (torch.logdet(2 * math.pi * LLT) * xs.shape[-2]).to(dev)
         v = white @ self.B.to(dev)
-        Rs, Os = self._precision_blocks(ts)
-        prior_logdet = det(decompose(Rs, Os))
-        K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift.to(dev), Os=Os, x=v)
+        if FUSED_PRIOR_LOGDET:
+            # ONE pass over the gaps gives the posterior precision K = Sigma^{-1} + shift AND log det Sigma^{-1} (the reference
+            # factorises both matrices, models.py:349-367): one cyclic reduction instead of two, forward and backward
+            Rs, Os, prior_logdet = self._precision_blocks(ts, shift, logdet=True)
+            K_mahal, K_logdet = mahal_and_det(Rs=Rs, Os=Os, x=v)
+            prior_logdet = prior_logdet.to(K_logdet.dtype)
+        else:
+            Rs, Os = self._precision_blocks(ts)
+            prior_logdet = det(decompose(Rs, Os))
+            K_mahal, K_logdet = mahal_and_det(Rs=Rs + shift.to(dev), Os=Os, x=v)
         return (-0.5 * ((obs_mahal - K_mahal) + (obs_logdet + K_logdet - prior_logdet))).to(ts.device)
 
     # ---- predictions at new times (reference models.py:394-546), vectorised over the targets

@@ -18,8 +18,9 @@ from . import _engine, _native
 EIG_COND_MAX = 1e7      # beyond this the eigen-form of exp(-d/2 G) loses too many digits: use torch.matrix_exp
 
 
-def peg_precision_torch(gaps, G, shift=None):
-    """Reference formulas in torch ops (differentiable by autograd): gaps (..., n-1) -> Rs (..., n, l, l), Os (..., n-1, l, l)."""
+def peg_precision_torch(gaps, G, shift=None, logdet=False):
+    """Reference formulas in torch ops (differentiable by autograd): gaps (..., n-1) -> Rs (..., n, l, l), Os (..., n-1, l, l)
+    [, log det of the unshifted block-tridiagonal matrix (...,), see peg_precision]."""
     eye = torch.eye(G.shape[0], dtype=G.dtype, device=G.device)
     A = torch.matrix_exp(-0.5 * G * gaps.to(G.dtype).unsqueeze(-1).unsqueeze(-1))
     At = A.transpose(-1, -2)
@@ -28,10 +29,13 @@ def peg_precision_torch(gaps, G, shift=None):
     from_prev, to_next = A @ bwd, At @ fwd
     base = eye if shift is None else eye + shift
     if gaps.shape[-1] == 0:
-        return base.expand(gaps.shape[:-1] + (1,) + tuple(base.shape)).clone(), -fwd
-    diag = torch.cat([base + to_next[..., :1, :, :], base + from_prev[..., :-1, :, :] + to_next[..., 1:, :, :],
-                      base + from_prev[..., -1:, :, :]], dim=-3)
-    return diag, -fwd
+        diag = base.expand(gaps.shape[:-1] + (1,) + tuple(base.shape)).clone()
+    else:
+        diag = torch.cat([base + to_next[..., :1, :, :], base + from_prev[..., :-1, :, :] + to_next[..., 1:, :, :],
+                          base + from_prev[..., -1:, :, :]], dim=-3)
+    if not logdet:
+        return diag, -fwd
+    return diag, -fwd, -torch.linalg.slogdet(eye - A @ At)[1].sum(-1)
 
 
 class _EigConsts:
@@ -88,20 +92,27 @@ class _EigConsts:
         self.rows = rows
         self.V, self.Vinv = V.to(dev), Vinv.to(dev)
         self.invdl, self.deg = invdl.to(dev), deg.to(dev)
+        if self.folded:
+            # index form of `rows` for the device: row 2l of the (zero-extended) S stands for "no imaginary part"; eigenvalue m >= nterms
+            # is the conjugate of its partner
+            z = 2 * l
+            ridx = [[q[0] for q in rows], [q[1] for q in rows]]
+            iidx = [[q[2] if q[2] >= 0 else z for q in rows], [q[3] if q[3] >= 0 else z for q in rows]]
+            src = list(range(nt)) + [self.partner[m] for m in range(nt, l)]
+            self.re_idx = torch.tensor([[ridx[w][m] for m in src] for w in range(2)], device=dev)
+            self.im_idx = torch.tensor([[iidx[w][m] for m in src] for w in range(2)], device=dev)
+            self.im_sign = torch.tensor([1.0] * nt + [-1.0] * (l - nt), dtype=torch.float64, device=dev).view(1, l, 1, 1)
+            self.diag = torch.arange(l, device=dev)
 
     def finish_expm_adjoint(self, S):
-        """S (2l, l, l) from crb200_peg_precision_bwd -> gG (l, l) real.  T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V for all l
+        """S (2l [+1], l, l) from crb200_peg_precision_bwd -> gG (l, l) real.  T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V for all l
         eigenvalues (conjugates by conjugation), Z_jk = (T_j - T_k)[k, j] / (lam_j - lam_k), the c-weighted sums on the
         diagonal and for equal eigenvalues, gG = Re(V^{-T} Z V^T) (Daleckii-Krein)."""
         l = self.V.shape[0]
-        Sc = torch.zeros((2, l, l, l), dtype=torch.complex128, device=S.device)       # [plain | c-weighted][m]
-        for m, (r0, r1, i0, i1) in enumerate(self.rows):
-            Sc[0, m] = torch.complex(S[r0], S[i0] if i0 >= 0 else torch.zeros_like(S[r0]))
-            Sc[1, m] = torch.complex(S[r1], S[i1] if i1 >= 0 else torch.zeros_like(S[r1]))
-        for m in range(self.nterms, l):
-            Sc[:, m] = Sc[:, self.partner[m]].conj()
+        Sx = torch.cat([S[:2 * l], torch.zeros_like(S[:1])])
+        Sc = torch.complex(Sx[self.re_idx], Sx[self.im_idx] * self.im_sign)           # [plain | c-weighted][m] (l, l)
         Tm = self.Vinv @ Sc @ self.V                                                  # (2, m, k, j)
-        idx = torch.arange(l, device=S.device)
+        idx = self.diag
         Tj = Tm[0][idx, :, idx]                                                       # [j, k] = T_j[k, j]
         Tk = torch.einsum("kkj->jk", Tm[0])                                           # [j, k] = T_k[k, j]
         Tc = Tm[1][idx, :, idx]                                                       # [j, k] = T'_j[k, j]
@@ -111,44 +122,52 @@ class _EigConsts:
 
 class _PegFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gaps, G, shift, consts):
+    def forward(ctx, gaps, G, shift, consts, want_logdet):
         B, nm1 = gaps.shape
         n, l, dtype, dev = nm1 + 1, G.shape[0], gaps.dtype, gaps.device
         R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
         O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
         info = torch.zeros(1, dtype=torch.int32, device=dev)
+        ld = torch.zeros(B, dtype=torch.float64, device=dev)
         sh = shift.detach().to(dev, torch.float64).contiguous() if shift is not None else None
         _native.peg_fwd(dtype, l, batch=B, n=n, gaps=gaps if nm1 > 0 else None, stride_gaps=gaps.stride(0) if nm1 > 0 else 0,
                         lam_re=consts.lam_re, lam_im=consts.lam_im, M_re=consts.M_re, M_im=consts.M_im, shift=sh,
-                        R=R, O=O if nm1 > 0 else None, strideR=n * l * l, strideO=nm1 * l * l, info=info, nterms=consts.nterms)
+                        R=R, O=O if nm1 > 0 else None, strideR=n * l * l, strideO=nm1 * l * l, info=info, nterms=consts.nterms,
+                        logdet=ld if want_logdet else None)
         ctx.consts, ctx.meta = consts, (B, n, l, dtype)
         ctx.save_for_backward(gaps, O)
         ctx.G_meta = (G.device, G.dtype)
         ctx.shift_meta = (shift.device, shift.dtype) if shift is not None else None
         ctx.info = info
-        return R, O
+        ctx.want_logdet = want_logdet
+        if not want_logdet:
+            ctx.mark_non_differentiable(ld)
+        return R, O, ld
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, gR, gO):
+    def backward(ctx, gR, gO, gld):
         gaps, O = ctx.saved_tensors
         B, n, l, dtype = ctx.meta
         c = ctx.consts
         dev = gaps.device
         gG = gshift = None
         if ctx.needs_input_grad[1]:
-            S = torch.zeros((2 * l, l, l), dtype=torch.float64, device=dev)
+            S = torch.zeros((2 * l + 1, l, l), dtype=torch.float64, device=dev)
             if n > 1:
                 gRc = _engine._rows_contiguous(gR.to(dtype))
                 gOc = _engine._rows_contiguous(gO.to(dtype))
+                gl = gld.to(torch.float64).contiguous() if ctx.want_logdet else None
                 _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
                                 lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im,
                                 O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), S=S,
-                                nterms=c.nterms)
+                                nterms=c.nterms, g_logdet=gl)
             gG = c.finish_expm_adjoint(S).to(*ctx.G_meta)
-        if ctx.shift_meta is not None and ctx.needs_input_grad[2]:
+            if n > 1 and ctx.shift_meta is not None and ctx.needs_input_grad[2]:
+                gshift = S[2 * l].to(*ctx.shift_meta)              # the kernel sums the gR rows it stages anyway
+        if gshift is None and ctx.shift_meta is not None and ctx.needs_input_grad[2]:
             gshift = gR.sum(dim=(0, 1), dtype=torch.float64).to(*ctx.shift_meta)
-        return None, gG, gshift, None
+        return None, gG, gshift, None, None
 
 
 _consts_cache = {}
@@ -170,18 +189,28 @@ def device_builder_available(rank: int) -> bool:
     return torch.cuda.is_available() and rank <= _native.peg_max_ell()
 
 
-def peg_precision(gaps, G, shift=None, check=True):
+def peg_precision(gaps, G, shift=None, check=True, logdet=False):
     """gaps (B, n-1) or (n-1,) on a CUDA device (float32 / float64 = the dtype of the blocks), G (l,l) and shift (l,l)
-    anywhere (they are tiny): returns (Rs, Os) on the device of `gaps`.  Differentiable wrt G and shift."""
+    anywhere (they are tiny): returns (Rs, Os) on the device of `gaps`.  Differentiable wrt G and shift.
+
+    ``logdet=True`` also returns log det of the UNSHIFTED block-tridiagonal matrix of every series, (B,) float64: the blocks
+    are the joint precision of the Markov chain z_1 ~ N(0, I), z_{g+1} | z_g ~ N(A_g z_g, I - A_g A_g^T) for ANY A_g (P = I + B A^T
+    = (I - A A^T)^{-1} is an identity), so its determinant is prod_g det(I - A_g A_g^T)^{-1}, and the kernel already holds the
+    Cholesky factor of every I - A_g A_g^T.  This is the `prior_logdet` of LEGFamily.log_likelihood, for which the reference
+    runs a second cyclic reduction (models.py:349-353); it is differentiable (its cotangent adds 2 g B_g to the cotangent of A_g)."""
     single = gaps.dim() == 1
     g2 = gaps.unsqueeze(0) if single else gaps
-    if not (g2.is_cuda and device_builder_available(G.shape[0])):
-        Gd = G.to(g2.device, g2.dtype)
-        R, O = peg_precision_torch(g2, Gd, shift.to(g2.device, g2.dtype) if shift is not None else None)
-    else:
+    use_torch = not (g2.is_cuda and device_builder_available(G.shape[0]))
+    if not use_torch:
         consts = _consts_for(G, g2.device)
-        if consts.cond > EIG_COND_MAX or not consts.folded:
-            R, O = peg_precision_torch(g2, G.to(g2.device, g2.dtype), shift.to(g2.device, g2.dtype) if shift is not None else None)
-        else:
-            R, O = _PegFn.apply(g2.contiguous(), G, shift, consts)
-    return (R[0], O[0]) if single else (R, O)
+        use_torch = consts.cond > EIG_COND_MAX or not consts.folded
+    if use_torch:
+        Gd = G.to(g2.device, g2.dtype)
+        out = peg_precision_torch(g2, Gd, shift.to(g2.device, g2.dtype) if shift is not None else None, logdet=logdet)
+        if logdet:
+            out = (out[0], out[1], out[2].to(torch.float64))
+    else:
+        out = _PegFn.apply(g2.contiguous(), G, shift, consts, logdet)
+        if not logdet:
+            out = out[:2]
+    return tuple(t[0] for t in out) if single else tuple(out)

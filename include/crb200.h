@@ -166,7 +166,7 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* args, void
  * ACCUMULATED into -- zero S first).  Rows, in order, for every m < nterms: Re e^{c lam_m}, c Re e^{c lam_m}, and if lam_im[m] != 0
  * also Im e^{c lam_m}, c Im e^{c lam_m} (conjugate pairs folded: always 2*l rows).  The caller finishes the adjoint of the matrix
  * exponential: T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V, Z_jk = (T_j - T_k)[k][j] / (lam_j - lam_k) (the c-weighted sum where the
- * eigenvalues coincide), gG = Re(V^{-T} Z V^T); the cotangent of `shift` is sum_i gR_i.
+ * eigenvalues coincide), gG = Re(V^{-T} Z V^T).  Row 2*l of S is sum_i gR_i, the cotangent of `shift`.
  * info (may be NULL): set to 1 if some I - A A^T was not positive definite (a non-positive gap). */
 typedef struct crb200_peg_fwd_args {
   int batch, n;
@@ -179,6 +179,10 @@ typedef struct crb200_peg_fwd_args {
   int nterms;                                          /* 0 = ell.  exp(cG) - I = Re sum_{k < nterms} (e^{c lam_k} - 1) M_k: a caller that folds
                                                           every conjugate pair of eigenvalues into one term (M_k doubled, partner dropped)
                                                           passes fewer than ell terms and halves the work of the expansion */
+  double* logdet;                                      /* (batch) or NULL: ACCUMULATES log det of the block-tridiagonal matrix (R without shift, O)
+                                                          of every series = -sum_g logdet(I - A_g A_g^T), from the Cholesky factors the kernel forms
+                                                          anyway.  It is the `prior_logdet` the reference gets from a second cyclic reduction
+                                                          (models.py:349-353: det(decompose(Sigma^{-1}))); zero it first */
 } crb200_peg_fwd_args;
 
 typedef struct crb200_peg_bwd_args {
@@ -187,8 +191,9 @@ typedef struct crb200_peg_bwd_args {
   const double* lam_re; const double* lam_im; const double* M_re; const double* M_im;   /* as in crb200_peg_fwd_args */
   const void* O; long long strideO;                    /* the forward result */
   const void* gR; const void* gO; long long stride_gR, stride_gO;
-  double* S;                                           /* (2*ell, ell*ell) doubles, ACCUMULATED into: see above */
+  double* S;                                           /* (2*ell + 1, ell*ell) doubles, ACCUMULATED into: see above; the last row is sum_i gR_i */
   int nterms;                                          /* as in crb200_peg_fwd_args */
+  const double* g_logdet;                              /* (batch) or NULL: cotangent of the forward's logdet output (adds 2 g B_g to gA_g) */
 } crb200_peg_bwd_args;
 
 int crb200_peg_precision_fwd(int dtype, int ell, const crb200_peg_fwd_args* args, void* stream);

@@ -74,3 +74,52 @@ def test_degenerate_eigenvalues_and_regular_spacing():
     (R1.sum() + (O1 ** 2).sum()).backward()
     assert_close(R1, R0, 1e-11, "Rs")
     assert_close(Gd.grad, Gr.grad, 1e-9, "gG degenerate")
+
+
+@pytest.mark.parametrize("dtype,tol_f,tol_g", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 1e-4)])
+@pytest.mark.parametrize("l", [1, 2, 3, 5, 8])
+def test_builder_logdet_is_the_prior_logdet_of_the_reference(l, dtype, tol_f, tol_g):
+    """logdet=True: log det of the unshifted block-tridiagonal precision as a by-product of the builder.  The
+    reference obtains the same number from a second cyclic reduction, det(decompose(Sigma^{-1})) (models.py:349-353): compared
+    here with the oracle's CR on the CPU, and its gradient (mixed with cotangents on Rs, Os) with torch autograd."""
+    from oracle import cr_oracle as orc
+    from cyclic_gps.peg import peg_precision, peg_precision_torch
+    for (B, n, seed) in ((1, 2, 1), (3, 33, 2), (2, 100, 3), (4, 64, 4), (1, 1, 5)):
+        G, shift = _model_G(l, 10 * l + seed)
+        gen = torch.Generator().manual_seed(seed)
+        gaps = -torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64)) + 0.02
+        Gr, sr = G.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+        R0, O0, ld0 = peg_precision_torch(gaps, Gr, sr, logdet=True)
+        Rp, Op = peg_precision_torch(gaps, G, None)
+        for b in range(B):                                            # the identity itself: closed form == CR log-determinant
+            want = orc.logdet(orc.factor(Rp[b], Op[b])) if n > 1 else torch.logdet(Rp[b, 0])
+            assert abs(float(ld0[b].detach()) - float(want)) <= 1e-10 * max(1.0, abs(float(want))), (float(ld0[b].detach()), float(want))
+        cR = torch.randn(R0.shape, generator=gen, dtype=torch.float64)
+        cR = cR + cR.transpose(-1, -2)
+        cO = torch.randn(O0.shape, generator=gen, dtype=torch.float64)
+        cl = torch.randn(B, generator=gen, dtype=torch.float64)
+        ((R0 * cR).sum() + (O0 * cO).sum() + (ld0 * cl).sum()).backward()
+        Gd, sd = G.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+        R1, O1, ld1 = peg_precision(gaps.to(dtype).cuda(), Gd, sd, logdet=True)
+        assert ld1.dtype == torch.float64 and tuple(ld1.shape) == (B,)
+        assert_close(R1, R0, tol_f, f"Rs l={l} B={B} n={n}")
+        if n > 1:
+            # every pivot of chol(I - A A^T) carries one rounding error of the storage type: for large gaps the pivots are ~1 and a
+            # gap's own log-determinant ~0, so the fp32 bound has an absolute part per pivot (the CR route has the same one)
+            slack = 0.0 if dtype == torch.float64 else 2e-7 * l * (n - 1)
+            err = float((ld1.detach().cpu() - ld0.detach()).abs().max())
+            assert err <= tol_f * float(ld0.detach().abs().max()) + slack, (f"logdet l={l} B={B} n={n}", err, ld0)
+        else:
+            assert float(ld1.detach().abs().max()) == 0.0
+        ((R1 * cR.to(dtype).cuda()).sum() + (O1 * cO.to(dtype).cuda()).sum() + (ld1 * cl.cuda()).sum()).backward()
+        assert_close(sd.grad, sr.grad, tol_g, f"g shift l={l} n={n}")
+        if n > 1:
+            assert_close(Gd.grad, Gr.grad, tol_g, f"gG l={l} B={B} n={n}")
+    # only the log-determinant is used (no cotangent reaches Rs / Os)
+    G, shift = _model_G(l, 77)
+    gaps = torch.rand((2, 50), dtype=torch.float64, generator=torch.Generator().manual_seed(9)) + 0.05
+    Gr = G.clone().requires_grad_(True)
+    peg_precision_torch(gaps, Gr, None, logdet=True)[2].sum().backward()
+    Gd = G.clone().requires_grad_(True)
+    peg_precision(gaps.to(dtype).cuda(), Gd, None, logdet=True)[2].sum().backward()
+    assert_close(Gd.grad, Gr.grad, tol_g, "gG from logdet alone")
