@@ -5,6 +5,7 @@
 #include <atomic>
 #include "crb200.h"
 #include "cr_multi.h"
+#include <cstdlib>
 
 namespace crb200 {
 #define CRB_DECL(TN, LO, HI)                                                                         \
@@ -70,6 +71,13 @@ bool batch_fits_one_wave(int batch) {
   return batch <= 2 * v;
 }
 
+// Large batches: fuse the single-tile levels into one launch of single-warp CTAs (CRB200_FUSE_LARGE=0 keeps a launch per level;
+// read once).
+bool fuse_large_batches() {
+  static const bool on = [] { const char* e = getenv("CRB200_FUSE_LARGE"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 // number of CR levels of an n-row system: floor(log2 n) + 1
 int max_levels(int n) {
   int L = 0;
@@ -78,15 +86,16 @@ int max_levels(int n) {
 }
 
 // First level of the fused tail of a sweep over levels 0..L-1 of an n-row system, or L when nothing is fused.
-// A level joins the tail when a series has at most 2 * kMultiWarps tiles of `tile` even nodes; the tail starts at
+// A level joins the tail when a series has at most `max_tiles` tiles of `tile` even nodes (2 * kMultiWarps for the four-warp CTAs
+// of small batches, 1 for the single-warp CTAs of large batches); the tail starts at
 // level 3 or deeper (the ping-pong scratch of the caller then has room for every fused level at its own offset, so
 // CTAs of different series never touch the same bytes), holds at least two and at most kMultiMax levels.
-int fuse_start(int n, int L, int tile, bool odd_parity_needed, int parity) {
+int fuse_start(int n, int L, int tile, bool odd_parity_needed, int parity, int max_tiles) {
   if (tile <= 0 || L < 5) return L;
   int ks = L, m = n;
   for (int k = 0; k < L; ++k, m /= 2) {
     const int E = (m + 1) / 2;
-    if (k >= 3 && (E + tile - 1) / tile <= 2 * crb200::kMultiWarps) { ks = k; break; }
+    if (k >= 3 && (E + tile - 1) / tile <= max_tiles) { ks = k; break; }
   }
   if (L - ks > crb200::kMultiMax) ks = L - crb200::kMultiMax;
   if (odd_parity_needed && ((ks & 1) != parity)) ++ks;
@@ -172,16 +181,20 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
   // writes its reduced system at its own offset of the ping-pong scratch: [0, B*m_ks) rows of slot (ks-1)&1 hold the
   // live input of level ks, and when the sweep stops early the result of the last level must sit at the base of
   // slot (L-1)&1 (that is where callers read it), which therefore has to be the OTHER slot: ks and L differ in parity.
-  int ks = a->nlevels;
+  int ks = a->nlevels, multi_warps = crb200::kMultiWarps;
   {
     const int L = a->nlevels;
     int mlast = a->n;
     for (int k = 0; k + 1 < L; ++k) mlast /= 2;
     const bool early = mlast / 2 > 0;                       // a system is left below level L-1
-    if (a->variant == CRB200_AUTO && a->batch > 0 && batch_fits_one_wave(a->batch) && fwd_multi(dtype, ell, nullptr, s) == cudaSuccess)
-      ks = fuse_start(a->n, L, crb200_fwd_tile_nodes(dtype, ell), early, (L & 1) ^ 1);
+    if (a->variant == CRB200_AUTO && a->batch > 0 && (batch_fits_one_wave(a->batch) || fuse_large_batches()) &&
+        fwd_multi(dtype, ell, nullptr, s) == cudaSuccess) {
+      multi_warps = batch_fits_one_wave(a->batch) ? crb200::kMultiWarps : 1;
+      ks = fuse_start(a->n, L, crb200_fwd_tile_nodes(dtype, ell), early, (L & 1) ^ 1, multi_warps == 1 ? 1 : 2 * crb200::kMultiWarps);
+    }
   }
   crb200::MultiArgs<crb200_fwd_args> multi{};
+  multi.warps = multi_warps;
   long long cum[2] = {0, 0};                                // rows already claimed in each scratch slot (fused levels)
   for (int k = 0; k < a->nlevels; ++k) {
     if (m < 1) return CRB200_EINVAL;
@@ -290,10 +303,14 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // fused tail: the deepest levels (L-1 .. ks) run in ONE launch, each writing its (Sigma_d, Sigma_o, w) at its own
   // offset of the ping-pong scratch (levels >= 3 together need less than a third of a slot)
-  int ks = a->nlevels;
-  if (a->variant == CRB200_AUTO && a->batch > 0 && batch_fits_one_wave(a->batch) && bwd_multi(dtype, ell, nullptr, s) == cudaSuccess)
-    ks = fuse_start(a->n, a->nlevels, crb200_bwd_tile_nodes(dtype, ell), false, 0);
+  int ks = a->nlevels, multi_warps = crb200::kMultiWarps;
+  if (a->variant == CRB200_AUTO && a->batch > 0 && (batch_fits_one_wave(a->batch) || fuse_large_batches()) &&
+      bwd_multi(dtype, ell, nullptr, s) == cudaSuccess) {
+    multi_warps = batch_fits_one_wave(a->batch) ? crb200::kMultiWarps : 1;
+    ks = fuse_start(a->n, a->nlevels, crb200_bwd_tile_nodes(dtype, ell), false, 0, multi_warps == 1 ? 1 : 2 * crb200::kMultiWarps);
+  }
   crb200::MultiArgs<crb200_bwd_args> multi{};
+  multi.warps = multi_warps;
   long long cum[2] = {0, 0};
   for (int k = a->nlevels - 1; k >= 0; --k) {
     const int m = ms[k];

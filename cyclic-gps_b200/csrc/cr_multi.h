@@ -1,5 +1,7 @@
 // Deep levels of a sweep fused into one launch (cr_tpn_*_multi_kernel): the per-level argument blocks travel as
-// ONE kernel parameter, one CTA of kMultiWarps warps per series.  Shared by the kernels and the ABI (host code).
+// ONE kernel parameter, one CTA per series: kMultiWarps warps for small batches (levels with up to 2 * kMultiWarps tiles per
+// series), ONE warp for large batches (only the levels that are a single tile per series: there a launch per level is pure
+// latency, and a single-warp CTA costs a series no more than its own tile).  Shared by the kernels and the ABI (host code).
 #pragma once
 
 namespace crb200 {
@@ -10,7 +12,7 @@ constexpr int kMultiWarps = 4;
 template <typename Args>
 struct MultiArgs {
   int count;
-  int pad_;
+  int warps;        // warps per CTA: kMultiWarps or 1
   Args lv[kMultiMax];
 };
 

@@ -476,8 +476,8 @@ cr_tpn_bwd_kernel(const LevelBwdArgs a) {
 }
 
 // Deep levels fused (deepest first): one CTA per series, see cr_tpn_fwd_multi_kernel.
-template <typename T, int L>
-__global__ void __launch_bounds__(32 * kMultiWarps, 1)
+template <typename T, int L, int NWM>
+__global__ void __launch_bounds__(32 * NWM, 1)
 cr_tpn_bwd_multi_kernel(const __grid_constant__ MultiArgs<LevelBwdArgs> ma) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -486,7 +486,7 @@ cr_tpn_bwd_multi_kernel(const __grid_constant__ MultiArgs<LevelBwdArgs> ma) {
     const LevelBwdArgs& a = ma.lv[k];
     const int E = (a.m + 1) >> 1;
     const int tiles = (E + TpnBwdCfg<T, L>::NT - 1) / TpnBwdCfg<T, L>::NT;
-    for (int tile = warp; tile < tiles; tile += kMultiWarps) {
+    for (int tile = warp; tile < tiles; tile += NWM) {
       tpn_bwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnBwdCfg<T, L>::SMEM_W, b, tile);
       __syncwarp();
     }
@@ -509,15 +509,19 @@ cudaError_t launch_tpn_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <typename T, int L, int NWM>
+cudaError_t launch_tpn_bwd_multi_w(const MultiArgs<LevelBwdArgs>& ma, cudaStream_t stream) {
+  using C = TpnBwdCfg<T, L>;
+  constexpr int SMEM = (int)(C::SMEM_W * NWM);
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_bwd_multi_kernel<T, L, NWM>, SMEM, attr_done); e != cudaSuccess) return e;
+  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
+  cr_tpn_bwd_multi_kernel<T, L, NWM><<<(unsigned)ma.lv[0].batch, 32 * NWM, SMEM, stream>>>(ma);
+  return cudaGetLastError();
+}
 template <typename T, int L>
 cudaError_t launch_tpn_bwd_multi(const MultiArgs<LevelBwdArgs>& ma, cudaStream_t stream) {
-  using C = TpnBwdCfg<T, L>;
-  constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
-  static std::atomic<unsigned char> attr_done[kMaxDevices];
-  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_bwd_multi_kernel<T, L>, SMEM, attr_done); e != cudaSuccess) return e;
-  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
-  cr_tpn_bwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
-  return cudaGetLastError();
+  return ma.warps == 1 ? launch_tpn_bwd_multi_w<T, L, 1>(ma, stream) : launch_tpn_bwd_multi_w<T, L, kMultiWarps>(ma, stream);
 }
 
 }  // namespace crb200

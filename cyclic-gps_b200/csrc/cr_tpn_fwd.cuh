@@ -404,8 +404,8 @@ cr_tpn_fwd_kernel(const LevelFwdArgs a) {
 // Deep levels fused: ONE CTA per series runs levels lv[0..count) back to back, its warps sharing the tiles of a
 // level; levels communicate through global memory (L2) and a __syncthreads.  Used by crb200_sweep_fwd for the
 // levels with only a few tiles per series, where a launch per level costs more than its work.
-template <typename T, int L>
-__global__ void __launch_bounds__(32 * kMultiWarps, 1)
+template <typename T, int L, int NWM>
+__global__ void __launch_bounds__(32 * NWM, 1)
 cr_tpn_fwd_multi_kernel(const __grid_constant__ MultiArgs<LevelFwdArgs> ma) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -414,7 +414,7 @@ cr_tpn_fwd_multi_kernel(const __grid_constant__ MultiArgs<LevelFwdArgs> ma) {
     const LevelFwdArgs& a = ma.lv[k];
     const int E = (a.m + 1) >> 1;
     const int tiles = (E + TpnFwdCfg<T, L>::OWN - 1) / TpnFwdCfg<T, L>::OWN;
-    for (int tile = warp; tile < tiles; tile += kMultiWarps) {
+    for (int tile = warp; tile < tiles; tile += NWM) {
       tpn_fwd_tile<T, L>(a, smem_raw + (size_t)warp * TpnFwdCfg<T, L>::SMEM_W, b, tile);
       __syncwarp();
     }
@@ -437,15 +437,19 @@ cudaError_t launch_tpn_fwd(const LevelFwdArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <typename T, int L, int NWM>
+cudaError_t launch_tpn_fwd_multi_w(const MultiArgs<LevelFwdArgs>& ma, cudaStream_t stream) {
+  using C = TpnFwdCfg<T, L>;
+  constexpr int SMEM = (int)(C::SMEM_W * NWM);
+  static std::atomic<unsigned char> attr_done[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_fwd_multi_kernel<T, L, NWM>, SMEM, attr_done); e != cudaSuccess) return e;
+  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
+  cr_tpn_fwd_multi_kernel<T, L, NWM><<<(unsigned)ma.lv[0].batch, 32 * NWM, SMEM, stream>>>(ma);
+  return cudaGetLastError();
+}
 template <typename T, int L>
 cudaError_t launch_tpn_fwd_multi(const MultiArgs<LevelFwdArgs>& ma, cudaStream_t stream) {
-  using C = TpnFwdCfg<T, L>;
-  constexpr int SMEM = (int)(C::SMEM_W * kMultiWarps);
-  static std::atomic<unsigned char> attr_done[kMaxDevices];
-  if (cudaError_t e = ensure_dynamic_smem(cr_tpn_fwd_multi_kernel<T, L>, SMEM, attr_done); e != cudaSuccess) return e;
-  if (ma.count <= 0 || ma.lv[0].batch <= 0) return cudaSuccess;
-  cr_tpn_fwd_multi_kernel<T, L><<<(unsigned)ma.lv[0].batch, 32 * kMultiWarps, SMEM, stream>>>(ma);
-  return cudaGetLastError();
+  return ma.warps == 1 ? launch_tpn_fwd_multi_w<T, L, 1>(ma, stream) : launch_tpn_fwd_multi_w<T, L, kMultiWarps>(ma, stream);
 }
 
 }  // namespace crb200
