@@ -353,12 +353,54 @@ def mahal(decomp, y):
     return out.to(y.device)
 
 
+class _InverseBlocksFn(torch.autograd.Function):
+    """Selected inverse of an existing factorisation, differentiable wrt the (Rs, Os) handed to ``decompose`` (the
+    reference's autograd through ``inverse_blocks(decompose(Rs, Os))`` is the oracle).  Forward: the CUDA level kernels.
+    Backward: the adjoint recursion has no kernels of its own -- the recursion is re-evaluated with differentiable torch ops
+    on the device and reversed by torch autograd (``_adjoint.selected_inverse``)."""
+
+    @staticmethod
+    def forward(ctx, Rs, Os, decomp):
+        pack = decomp._pack
+        ctx.pack, ctx.batched, ctx.caller = pack, decomp._batched, Rs.device
+        ctx.save_for_backward(Rs, Os)
+        Sd, So, _ = _engine.backward_sweep(pack, sigma=True, w=False)
+        return _to_caller(Sd, decomp._batched, decomp._caller_device), _to_caller(So, decomp._batched, decomp._caller_device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gSd, gSo):
+        from . import _adjoint
+        Rs, Os = ctx.saved_tensors
+        dev, dtype = ctx.pack.device, ctx.pack.dtype
+        with torch.enable_grad():
+            R = _batched(_dev(Rs.detach(), dev, dtype), ctx.batched).clone().requires_grad_(True)
+            O = _batched(_dev(Os.detach(), dev, dtype), ctx.batched).clone().requires_grad_(True)
+            Sd, So = _adjoint.selected_inverse(R, O)
+            gR, gO = torch.autograd.grad((Sd, So), (R, O), (_batched(_dev(gSd, dev, dtype), ctx.batched), _batched(_dev(gSo, dev, dtype), ctx.batched)),
+                                         allow_unused=True)
+        gO = gO if gO is not None else torch.zeros_like(O)
+        return _to_caller(gR, ctx.batched, ctx.caller), _to_caller(gO, ctx.batched, ctx.caller), None
+
+
 def inverse_blocks(decomp):
     """Diagonal and lower off-diagonal blocks of J^{-1}  (reference :470-503):
-    ``(Sig_diag:(n,l,l), Sig_off:(n-1,l,l))`` with ``Sig_off[i] = (J^{-1})_{i+1,i}``."""
+    ``(Sig_diag:(n,l,l), Sig_off:(n-1,l,l))`` with ``Sig_off[i] = (J^{-1})_{i+1,i}``.  Differentiable wrt the ``Rs`` / ``Os``
+    that were handed to ``decompose`` when they require grad."""
     pack, batched, caller = _pack_of(decomp)
+    if isinstance(decomp, CRDecomp) and decomp._Rs is not None and torch.is_grad_enabled() and (decomp._Rs.requires_grad or decomp._Os.requires_grad):
+        return _InverseBlocksFn.apply(decomp._Rs, decomp._Os, decomp)
     Sd, So, _ = _engine.backward_sweep(pack, sigma=True, w=False)
     return _to_caller(Sd, batched, caller), _to_caller(So, batched, caller)
+
+
+def check_decompose_loop_outputs(num_dblocks, Ks_even, F, G, Rs, Os):
+    """Shape check of one level's outputs (reference :262-280; there only the even branch can fire -- the odd one is guarded by
+    ``!= 0 & num_dblocks > 1``, which parses as a chained comparison): E = ceil(m/2) factors, floor(m/2) F blocks and reduced
+    diagonal blocks, floor((m-1)/2) G blocks, floor(m/2) - 1 reduced off-diagonal blocks.  Raises AssertionError like the reference."""
+    E, o, g = _engine.counts(int(num_dblocks))
+    assert (Ks_even.shape[-3] == E and F.shape[-3] == o and G.shape[-3] == g and Rs.shape[-3] == o
+            and Os.shape[-3] == max(o - 1, 0)), "decompose_step outputs do not match the level's block counts"
 
 
 # ---------------------------------------------------------------------------------------

@@ -437,6 +437,52 @@ def test_solve_is_differentiable(l, n, dtype):
     assert_close(Og.grad, Oo.grad, tol, "d/dOs")
 
 
+@pytest.mark.parametrize("l,n,dtype,batched", [(1, 1, torch.float64, False), (2, 2, torch.float64, False), (3, 33, torch.float64, True),
+                                                (5, 100, torch.float64, False), (8, 257, torch.float32, True), (16, 40, torch.float64, False)])
+def test_inverse_blocks_is_differentiable(l, n, dtype, batched):
+    """gradient of a scalar function of inverse_blocks(decompose(Rs, Os)) wrt Rs, Os against torch autograd
+    through the oracle (= the reference's autograd path for the same expression, cyclic_reduction.py:470-503).  The forward
+    values come from the CUDA kernels, the backward from the torch-op adjoint recursion (cyclic_gps/_adjoint.py)."""
+    c = cr()
+    tol = TOL[dtype]
+    series = [leg_inputs(l, n, dtype, seed=9 * l + n + b) for b in range(3 if batched else 1)]
+    gen = torch.Generator().manual_seed(3)
+    gR_want, gO_want, Sd_want, So_want, cds, cos = [], [], [], [], [], []
+    for (R, O, _) in series:
+        Ro, Oo = R.double().clone().requires_grad_(True), O.double().clone().requires_grad_(True)
+        Sd0, So0 = orc.selected_inverse(orc.factor(Ro, Oo))
+        cd, co = torch.randn(Sd0.shape, generator=gen, dtype=torch.float64), torch.randn(So0.shape, generator=gen, dtype=torch.float64)
+        ((Sd0 * cd).sum() + (So0 * co).sum()).backward()
+        gR_want.append(Ro.grad); gO_want.append(Oo.grad if n > 1 else torch.zeros_like(Oo)); Sd_want.append(Sd0.detach()); So_want.append(So0.detach())
+        cds.append(cd); cos.append(co)
+    st = (lambda xs: torch.stack(xs)) if batched else (lambda xs: xs[0])
+    Rg = st([s[0] for s in series]).cuda().requires_grad_(True)
+    Og = st([s[1] for s in series]).cuda().requires_grad_(True)
+    Sd, So = c.inverse_blocks(c.decompose(Rg, Og))
+    assert Sd.requires_grad
+    ((Sd * st(cds).to(dtype).cuda()).sum() + (So * st(cos).to(dtype).cuda()).sum()).backward()
+    assert_close(Sd, st(Sd_want), tol, "Sigma_d")
+    assert_close(Rg.grad, st(gR_want), 10 * tol, "d/dRs")
+    if n > 1:
+        assert_close(So, st(So_want), tol, "Sigma_o")
+        assert_close(Og.grad, st(gO_want), 10 * tol, "d/dOs")
+    # no grad requested: the plain kernel path, nothing attached
+    Sd2, So2 = c.inverse_blocks(c.decompose(Rg.detach(), Og.detach()))
+    assert not Sd2.requires_grad
+    assert_close(Sd2, Sd.detach(), 0.0 if dtype == torch.float64 else tol, "same forward")
+
+
+def test_check_decompose_loop_outputs_like_the_reference():
+    """reference cyclic_reduction.py:262-280: the shape check of one level (AssertionError on a mismatch)."""
+    c = cr()
+    for n in (2, 5, 8):
+        R, O, _ = leg_inputs(3, n, torch.float64, seed=n)
+        (m, K, F, G), (Rn, On) = c.decompose_step(R, O)
+        c.check_decompose_loop_outputs(m, K, F, G, Rn, On)
+        with pytest.raises(AssertionError):
+            c.check_decompose_loop_outputs(m + 2, K, F, G, Rn, On)
+
+
 @pytest.mark.parametrize("l,n,dtype,batch", [(3, 1000, torch.float64, None), (8, 700, torch.float32, 6), (16, 300, torch.float64, 2)])
 def test_graphed_mahal_and_det_replays(l, n, dtype, batch):
     """cyclic_gps.graphs.GraphedMahalAndDet: a CUDA-graph replay gives the numbers of the eager path, for new inputs too."""

@@ -85,3 +85,29 @@ def test_intercast_vectorised_matches_reference_loop(golden):
         for ours, key in ((zm, "z_mean"), (zv, "z_cov")):
             ref = torch.from_numpy(g[p + key])
             assert float((ours - ref).abs().max() / ref.abs().max()) < 1e-10, (p, key)
+
+
+def test_adjoint_recursion_of_inverse_blocks_matches_oracle_autograd():
+    """cyclic_gps/_adjoint.py (torch-op restatement of the level recursion, used ONLY by the backward pass of
+    ``inverse_blocks``) against torch autograd through the oracle's factor + selected_inverse: values and raw gradients."""
+    from cyclic_gps._adjoint import selected_inverse
+    gen = torch.Generator().manual_seed(0)
+    for l in (1, 3, 8):
+        G, Bm, LLT = orc.leg_params(l, seed=3)
+        for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 33, 100):
+            gaps = -torch.log(torch.rand(max(n - 1, 1), generator=gen, dtype=torch.float64)) + 0.05
+            R, O = orc.leg_posterior_precision(gaps, G, Bm, LLT)
+            if n == 1:
+                R, O = R[:1].clone(), torch.zeros((0, l, l), dtype=torch.float64)
+            Rr, Or = R.clone().requires_grad_(True), O.clone().requires_grad_(True)
+            Sd0, So0 = orc.selected_inverse(orc.factor(Rr, Or))
+            cd, co = torch.randn(Sd0.shape, generator=gen, dtype=torch.float64), torch.randn(So0.shape, generator=gen, dtype=torch.float64)
+            ((Sd0 * cd).sum() + (So0 * co).sum()).backward()
+            R2, O2 = R.clone().requires_grad_(True), O.clone().requires_grad_(True)
+            Sd, So = selected_inverse(R2[None], O2[None])
+            ((Sd[0] * cd).sum() + (So[0] * co).sum()).backward()
+            assert_close(Sd[0], Sd0, 1e-11, f"Sigma_d l={l} n={n}")
+            assert_close(R2.grad, Rr.grad, 1e-10, f"gR l={l} n={n}")
+            if n > 1:
+                assert_close(So[0], So0, 1e-11, f"Sigma_o l={l} n={n}")
+                assert_close(O2.grad, Or.grad, 1e-10, f"gO l={l} n={n}")
