@@ -501,8 +501,17 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
         del Rb, Ob
 
     copy_stream = torch.cuda.Stream(device=dev)
-    nchunk = args.e2e_chunks if (B % args.e2e_chunks == 0 and B >= 64) else 1
-    bsz = B // nchunk
+    # chunk plan: a SMALL first chunk (its H2D copy is the only one nothing can hide), the rest in equal parts
+    if B >= 64 and args.e2e_chunks > 1:
+        first = max(1, B // args.e2e_first_frac)
+        rest = args.e2e_chunks - 1
+        sizes = [first] + [(B - first) // rest + (1 if i < (B - first) % rest else 0) for i in range(rest)]
+    else:
+        sizes = [B]
+    bounds = [0]
+    for z in sizes:
+        bounds.append(bounds[-1] + z)
+    nchunk = len(sizes)
 
     def e2e_step():
         """The batch is cut into chunks of series: chunk c + 1 crosses PCIe on a copy stream while chunk c is built and reduced."""
@@ -511,7 +520,7 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
         ready = []
         with torch.cuda.stream(copy_stream):
             for c in range(nchunk):
-                sl = slice(c * bsz, (c + 1) * bsz)
+                sl = slice(bounds[c], bounds[c + 1])
                 d_ts[sl].copy_(h_ts[sl], non_blocking=True)
                 d_xs[sl].copy_(h_xs[sl], non_blocking=True)
                 ev = torch.cuda.Event()
@@ -519,7 +528,7 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
                 ready.append(ev)
         tot = torch.zeros((), dtype=torch.float64, device=dev)
         for c in range(nchunk):
-            sl = slice(c * bsz, (c + 1) * bsz)
+            sl = slice(bounds[c], bounds[c + 1])
             main_s.wait_event(ready[c])
             with torch.no_grad():
                 Rs, Os = model._precision_blocks(d_ts[sl], shift)
@@ -552,7 +561,7 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
     h2d = h_ts.numel() * 8 + h_xs.numel() * s
     e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
            "ms_per_step": ms2, "steps": k2,
-           "pipeline": f"{nchunk} chunks of {bsz} series, H2D on a copy stream under the compute of the previous chunk; "
+           "pipeline": f"chunks of {sizes} series, H2D on a copy stream under the compute of the previous chunk; "
                        "pinned host time stamps (fp64) + observations -> device; precision blocks built on the device "
                        "(crb200_peg_precision_fwd = the reference's compute_posterior_precision); cr.mahal_and_det + backward to gR, gO, gx; "
                        "per-series scalars -> host",
@@ -634,6 +643,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="e2e: chunks of series whose H2D copies overlap the previous chunk's compute")
+    ap.add_argument("--e2e-first-frac", type=int, default=8, help="e2e: the first chunk holds batch / this many series (its copy cannot overlap anything)")
     ap.add_argument("--no-long", action="store_true", help="skip the long_series object (configs[3])")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling run of configs[1]")
     ap.add_argument("--no-parity", action="store_true", help="long series: skip the parity block")

@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
   const int g = 31 * t - 1 + lane;                              // gap between rows g and g + 1 (virtual at both ends)
   const bool real = g >= 0 && g <= n - 2;
   const T* gaps = static_cast<const T*>(a.gaps) + (size_t)b * a.stride_gaps;
+  constexpr int RSF = record_stride<T>(L * L, L * L);            // staging record stride (elements)
+  T* wstage = reinterpret_cast<T*>(smem_raw + align16(sizeof(PegConsts<CT, L>))) + (size_t)warp * 32 * RSF;
+  T* myrec = wstage + (size_t)lane * RSF;
+  const unsigned srec0 = smem_u32(wstage), nsb = (unsigned)(RSF * sizeof(T));
 
   CT Pm1[L][L], Qm1[L][L];                  // P - I (-> row g + 1), Q - I (-> row g): symmetric, only the lower triangles (q <= r) are formed
 #pragma unroll
@@ -252,16 +256,25 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
         Pm1[r][q] = sp;
         Qm1[r][q] = sq;
       }
-    // O_g = -B  (lane 0's gap belongs to the previous warp's tile)
+    // O_g = -B into this lane's staging record (lane 0's gap belongs to the previous warp's tile)
     if (lane >= 1) {
-      T* Og = static_cast<T*>(a.O) + (size_t)b * a.strideO + (size_t)g * (L * L);
 #pragma unroll
-      for (int r = 0; r < L; ++r)
+      for (int r = 0; r < L; ++r) {
 #pragma unroll
         for (int q = 0; q < L; ++q) Bm[r][q] = -Bm[r][q];
-      peg_store_block<T, L>(Og, Bm, is_aligned16(static_cast<T*>(a.O) + (size_t)b * a.strideO));
+        sts_row<T, L>(myrec + r * L, Bm[r]);
+      }
     }
   }
+  // The results leave through a per-warp staging area (one padded record per lane) as flat, fully coalesced 16-byte stores:
+  // per-thread 256-byte block stores cost the LSU 32 sectors per instruction and made the kernel LSU-bound (ncu: STG = 20 % of the stalls).
+  __syncwarp();
+  {
+    const int g0 = 31 * t;                                        // first gap / row of this tile (lane 1)
+    T* Og = static_cast<T*>(a.O) + (size_t)b * a.strideO + (size_t)g0 * (L * L);
+    if (a.O != nullptr) rec_s2g<T, L * L, 1>(Og, srec0, nsb, 1, cmin(31, (n - 1) - g0), is_aligned16(Og));
+  }
+  __syncwarp();
   if (bad && a.info != nullptr) atomicMax(a.info, 1);
   if (a.logdet != nullptr) {                  // logdet of the whole block-tridiagonal precision = -sum_g logdet(I - A_g A_g^T)
 #pragma unroll
@@ -279,8 +292,14 @@ __global__ void __launch_bounds__(kPegThreads, sizeof(T) == 4 ? 3 : 1) cr_peg_fw
       if (q < r) Rr[q][r] = sym + S->shift[q * L + r];
     }
   if (lane >= 1 && g <= n - 1) {
-    T* Rg = static_cast<T*>(a.R) + (size_t)b * a.strideR + (size_t)g * (L * L);
-    peg_store_block<T, L>(Rg, Rr, is_aligned16(static_cast<T*>(a.R) + (size_t)b * a.strideR));
+#pragma unroll
+    for (int r = 0; r < L; ++r) sts_row<T, L>(myrec + r * L, Rr[r]);
+  }
+  __syncwarp();
+  {
+    const int g0 = 31 * t;
+    T* Rg = static_cast<T*>(a.R) + (size_t)b * a.strideR + (size_t)g0 * (L * L);
+    rec_s2g<T, L * L, 1>(Rg, srec0, nsb, 1, cmin(31, n - g0), is_aligned16(Rg));
   }
 }
 
@@ -624,7 +643,7 @@ __global__ void __launch_bounds__(PegBwdCfg<T, L>::NW * 32, 1) cr_peg_bwd_kernel
 
 template <typename T, int L>
 cudaError_t launch_peg_fwd(const PegFwdArgs& a, cudaStream_t stream) {
-  const size_t smem = sizeof(PegConsts<T, L>);
+  const size_t smem = align16(sizeof(PegConsts<T, L>)) + (size_t)kPegThreads * record_stride<T>(L * L, L * L) * sizeof(T);
   static std::atomic<unsigned char> attr_done[kMaxDevices];
   if (cudaError_t e = ensure_dynamic_smem(cr_peg_fwd_kernel<T, L>, (int)smem, attr_done); e != cudaSuccess) return e;
   const long long tiles = (long long)((a.n + 30) / 31) * a.batch;

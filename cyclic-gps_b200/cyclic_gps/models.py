@@ -20,6 +20,12 @@ from cyclic_gps.peg import peg_precision
 # a second factorisation as the reference does (models.py:349-353).  Same value (an algebraic identity, see peg.peg_precision).
 FUSED_PRIOR_LOGDET = True
 
+
+def _rows_times(x, W):
+    """x (..., n, d) @ W (d, k).  With a single observation channel (d = 1, the shape of the reference's timing scripts) the
+    product is a broadcast multiply: a GEMM with inner dimension 1 runs far below the memory roofline."""
+    return x * W.reshape(W.shape[-1]) if x.shape[-1] == 1 else x @ W
+
 try:  # pragma: no cover - not installed in the build image
     import pytorch_lightning as pl
     _Base = pl.LightningModule
@@ -148,7 +154,7 @@ class LEGFamily(_Base):
         """v = B^T (LL^T)^{-1} x for every row (reference models.py:270-280): the (d x l) map is formed once on the
         parameters' device, the per-row work is one matmul on the device of xs."""
         LLT = self.calc_Lambda_Lambda_T(self.Lambda)
-        return xs @ torch.linalg.solve(LLT, self.B).to(xs.device)
+        return _rows_times(xs, torch.linalg.solve(LLT, self.B).to(xs.device))
 
     def compute_insample_posterior(self, ts, xs):
         """Posterior mean (n,l) and {"Rs","Os"} blocks of the posterior covariance
@@ -174,10 +180,10 @@ class LEGFamily(_Base):
         dev = self._compute_device(ts)
         LLT, shift = self._obs_terms()
         xs_d = xs.to(dev)
-        white = xs_d @ torch.linalg.inv(LLT).to(dev)          # x^T (LL^T)^{-1} per row (LL^T is d x d and symmetric)
+        white = _rows_times(xs_d, torch.linalg.inv(LLT).to(dev))   # x^T (LL^T)^{-1} per row (LL^T is d x d and symmetric)
         obs_mahal = torch.sum(white * xs_d, dim=(-1, -2))
         obs_logdet = (torch.logdet(2 * math.pi * LLT) * xs.shape[-2]).to(dev)
-        v = white @ self.B.to(dev)
+        v = _rows_times(white, self.B.to(dev))
         if FUSED_PRIOR_LOGDET:
             # ONE pass over the gaps gives the posterior precision K = Sigma^{-1} + shift AND log det Sigma^{-1} (the reference
             # factorises both matrices, models.py:349-367): one cyclic reduction instead of two, forward and backward
