@@ -145,6 +145,16 @@ class LEGFamily(_Base):
         LLT = self.calc_Lambda_Lambda_T(self.Lambda)
         return LLT, self.B.T @ torch.linalg.solve(LLT, self.B)
 
+    def _obs_factor(self):
+        """(LL^T)^{-1}, W = (LL^T)^{-1} B, shift = B^T W and log det(2 pi LL^T) from ONE Cholesky of the d x d matrix, without the
+        device -> host status reads of three LU-based calls (solve / inv / logdet): at small n those calls are the step's cost."""
+        LLT = self.calc_Lambda_Lambda_T(self.Lambda)
+        C, _ = torch.linalg.cholesky_ex(LLT)
+        inv = torch.cholesky_inverse(C)
+        W = inv @ self.B
+        logdet = LLT.shape[0] * math.log(2 * math.pi) + 2 * torch.log(torch.diagonal(C)).sum()
+        return inv, W, self.B.T @ W, logdet
+
     def compute_posterior_precision(self, ts):
         _, shift = self._obs_terms()
         Rs, Os = self._precision_blocks(ts, shift)
@@ -178,12 +188,12 @@ class LEGFamily(_Base):
         the precision blocks are built there (``_precision_blocks``)."""
         self.register_model_matrices_from_params()
         dev = self._compute_device(ts)
-        LLT, shift = self._obs_terms()
+        LLT_inv, W, shift, logdet_2pi_LLT = self._obs_factor()
         xs_d = xs.to(dev)
-        white = _rows_times(xs_d, torch.linalg.inv(LLT).to(dev))   # x^T (LL^T)^{-1} per row (LL^T is d x d and symmetric)
+        white = _rows_times(xs_d, LLT_inv.to(dev))            # x^T (LL^T)^{-1} per row (LL^T is d x d and symmetric)
         obs_mahal = torch.sum(white * xs_d, dim=(-1, -2))
-        obs_logdet = (torch.logdet(2 * math.pi * LLT) * xs.shape[-2]).to(dev)
-        v = _rows_times(white, self.B.to(dev))
+        obs_logdet = (logdet_2pi_LLT * xs.shape[-2]).to(dev)
+        v = _rows_times(xs_d, W.to(dev))
         if FUSED_PRIOR_LOGDET:
             # ONE pass over the gaps gives the posterior precision K = Sigma^{-1} + shift AND log det Sigma^{-1} (the reference
             # factorises both matrices, models.py:349-367): one cyclic reduction instead of two, forward and backward

@@ -11,6 +11,7 @@ ships 4 bytes per row to the GPU instead of (2 l^2 + l) elements.
 G is eigendecomposed once per call on the host (l x l, as the reference's ``compute_eG`` does, model_utils.py:12-29).
 Block sizes above ``crb200_peg_max_ell()`` (8), an ill-conditioned eigenbasis or CPU-only use fall back to the same
 formulas in torch ops (``peg_precision_torch``), which is also the oracle of the tests."""
+import numpy as np
 import torch
 
 from . import _engine, _native
@@ -41,68 +42,66 @@ def peg_precision_torch(gaps, G, shift=None, logdet=False):
 class _EigConsts:
     """Everything the kernels need about G, as ONE device array of doubles (+ complex V, V^{-1} on the device)."""
 
-    def __init__(self, G, dev):
+    def __init__(self, G, dev, G_host=None):
+        # plain numpy on the host: for l x l matrices the per-call overhead of tensor ops is what this constructor costs
         l = G.shape[0]
-        Gc = G.detach().to(torch.float64).cpu()
-        lam, V = torch.linalg.eig(Gc)
-        self.cond = float(torch.linalg.cond(V))
+        Gc = (G_host if G_host is not None else G.detach().to("cpu", torch.float64)).numpy()
+        lam, V = np.linalg.eig(Gc)
+        lam, V = lam.astype(np.complex128), V.astype(np.complex128)
+        sv = np.linalg.svd(V, compute_uv=False)
+        self.cond = float(sv[0] / sv[-1]) if sv[-1] > 0 else float("inf")
         # Order the spectrum as [eigenvalues with Im > 0 | real eigenvalues | conjugates of the first group] and make the
         # conjugate columns of V exact conjugates (G is real): the expansion of exp(cG) - I then only needs the first
-        # `nterms` terms (complex ones doubled), and the kernel only produces the rows j < nterms of Z -- the others follow
-        # from Z[j', k'] = conj(Z[j, k]) with ' = conjugate partner.
-        tol = 1e-12 * float(lam.abs().max().clamp_min(1e-300))
-        pos = [k for k in range(l) if float(lam[k].imag) > tol]
-        real = [k for k in range(l) if abs(float(lam[k].imag)) <= tol]
-        if len(pos) + len(real) + len(pos) == l:
-            lam = torch.cat([lam[pos], lam[real].real.to(lam.dtype), lam[pos].conj()])
+        # `nterms` terms (complex ones doubled), and the kernel only accumulates the sums of one member of every pair.
+        tol = 1e-12 * max(float(np.abs(lam).max()), 1e-300)
+        pos = np.nonzero(lam.imag > tol)[0]
+        real = np.nonzero(np.abs(lam.imag) <= tol)[0]
+        npos, nreal = len(pos), len(real)
+        if 2 * npos + nreal == l:
+            lam = np.concatenate([lam[pos], lam[real].real.astype(np.complex128), lam[pos].conj()])
             Vr = V[:, real]
-            if len(real):                               # real eigenvalue -> real eigenvector (remove the arbitrary phase)
-                piv = Vr.abs().argmax(dim=0)
-                ph = Vr[piv, torch.arange(len(real))]
-                Vr = (Vr * (ph.conj() / ph.abs())).real.to(V.dtype)
-            V = torch.cat([V[:, pos], Vr, V[:, pos].conj()], dim=1)
-            self.nterms = len(pos) + len(real)
-            self.partner = list(range(self.nterms, l)) + list(range(len(pos), self.nterms)) + list(range(len(pos)))
-            weights = torch.tensor([2.0] * len(pos) + [1.0] * len(real), dtype=torch.float64)
+            if nreal:                                   # real eigenvalue -> real eigenvector (remove the arbitrary phase)
+                ph = Vr[np.abs(Vr).argmax(axis=0), np.arange(nreal)]
+                Vr = (Vr * (ph.conj() / np.abs(ph))).real.astype(np.complex128)
+            V = np.concatenate([V[:, pos], Vr, V[:, pos].conj()], axis=1)
+            self.nterms = nt = npos + nreal
+            self.partner = list(range(nt, l)) + list(range(npos, nt)) + list(range(npos))
+            weights = np.concatenate([np.full(npos, 2.0), np.ones(nreal)])
         else:                                           # (spectrum not closed under conjugation: cannot happen for a real G)
-            self.nterms, self.partner, weights = l, None, torch.ones(l, dtype=torch.float64)
-        Vinv = torch.linalg.inv(V)
-        M = torch.einsum("rk,kc->krc", V, Vinv).reshape(l, l * l)
-        nt = self.nterms
-        lam_t = torch.cat([lam[:nt], torch.zeros(l - nt, dtype=lam.dtype)])
-        M_t = torch.cat([M[:nt] * weights.unsqueeze(1), torch.zeros((l - nt, l * l), dtype=M.dtype)])
-        dl = lam.unsqueeze(1) - lam.unsqueeze(0)
-        deg = dl.abs() <= 1e-9 * lam.abs().max().clamp_min(1e-300)
-        invdl = torch.where(deg, torch.zeros_like(dl), 1.0 / torch.where(deg, torch.ones_like(dl), dl))
-        parts = [lam_t.real, lam_t.imag, M_t.real, M_t.imag]
-        flat = torch.cat([p.reshape(-1).to(torch.float64) for p in parts]).contiguous()
-        self.buf = flat.to(dev)
-        base, off, ptrs = self.buf.data_ptr(), 0, []
-        for p in parts:
-            ptrs.append(base + 8 * off)
-            off += p.numel()
-        self.lam_re, self.lam_im, self.M_re, self.M_im = ptrs
+            self.nterms = nt = l
+            self.partner, weights = None, np.ones(l)
+        Vinv = np.linalg.inv(V)
+        M = (V.T[:, :, None] * Vinv[:, None, :]).reshape(l, l * l)          # M_k = V[:, k] V^{-1}[k, :]
+        lam_t = np.concatenate([lam[:nt], np.zeros(l - nt, dtype=np.complex128)])
+        M_t = np.concatenate([M[:nt] * weights[:, None], np.zeros((l - nt, l * l), dtype=np.complex128)])
+        dl = lam[:, None] - lam[None, :]
+        deg = np.abs(dl) <= 1e-9 * max(float(np.abs(lam).max()), 1e-300)
+        invdl = np.where(deg, 0.0, 1.0 / np.where(deg, 1.0, dl))
+        flat = np.concatenate([lam_t.real, lam_t.imag, M_t.real.reshape(-1), M_t.imag.reshape(-1)])
+        self.buf = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+        base = self.buf.data_ptr()
+        self.lam_re, self.lam_im, self.M_re, self.M_im = base, base + 8 * l, base + 16 * l, base + 16 * l + 8 * l * l * l
         # host side of the backward pass (finish_expm_adjoint): which rows of the kernel's S belong to which eigenvalue
-        rows, r = [], 0
-        for m in range(nt):
-            cplx = float(lam_t[m].imag) != 0.0
-            rows.append((r, r + 1, r + 2 if cplx else -1, r + 3 if cplx else -1))
-            r += 4 if cplx else 2
-        self.folded = self.partner is not None and r == 2 * l
-        self.rows = rows
-        self.V, self.Vinv = V.to(dev), Vinv.to(dev)
-        self.invdl, self.deg = invdl.to(dev), deg.to(dev)
+        cplx = lam_t[:nt].imag != 0.0
+        r0 = np.concatenate([[0], np.cumsum(np.where(cplx, 4, 2))])
+        self.rows = [(int(r0[m]), int(r0[m]) + 1, int(r0[m]) + 2 if cplx[m] else -1, int(r0[m]) + 3 if cplx[m] else -1) for m in range(nt)]
+        self.folded = self.partner is not None and int(r0[-1]) == 2 * l
+        # three host -> device copies in all (small problems are bound by such calls): the doubles above, one complex pack, one index pack
+        cpack = torch.from_numpy(np.stack([V, Vinv, invdl.astype(np.complex128)])).to(dev)
+        self.V, self.Vinv, self.invdl = cpack[0], cpack[1], cpack[2]
+        self.deg = self.invdl == 0                                  # 1 / (lam_j - lam_k) is stored as 0 exactly where the pair is degenerate
         if self.folded:
             # index form of `rows` for the device: row 2l of the (zero-extended) S stands for "no imaginary part"; eigenvalue m >= nterms
             # is the conjugate of its partner
-            z = 2 * l
-            ridx = [[q[0] for q in rows], [q[1] for q in rows]]
-            iidx = [[q[2] if q[2] >= 0 else z for q in rows], [q[3] if q[3] >= 0 else z for q in rows]]
-            src = list(range(nt)) + [self.partner[m] for m in range(nt, l)]
-            self.re_idx = torch.tensor([[ridx[w][m] for m in src] for w in range(2)], device=dev)
-            self.im_idx = torch.tensor([[iidx[w][m] for m in src] for w in range(2)], device=dev)
-            self.im_sign = torch.tensor([1.0] * nt + [-1.0] * (l - nt), dtype=torch.float64, device=dev).view(1, l, 1, 1)
-            self.diag = torch.arange(l, device=dev)
+            src = np.array(list(range(nt)) + self.partner[nt:], dtype=np.int64)
+            base_r = r0[:-1][src]
+            im0 = np.where(cplx[src], base_r + 2, 2 * l)
+            im1 = np.where(cplx[src], base_r + 3, 2 * l)
+            ipack = np.stack([np.stack([base_r, base_r + 1]), np.stack([im0, im1]),
+                              np.stack([np.arange(l), np.concatenate([np.ones(nt), -np.ones(l - nt)]).astype(np.int64)])]).astype(np.int64)
+            ipack = torch.from_numpy(ipack).to(dev)
+            self.re_idx, self.im_idx, self.diag = ipack[0], ipack[1], ipack[2, 0]
+            self.im_sign = ipack[2, 1].to(torch.float64).view(1, l, 1, 1)
 
     def finish_expm_adjoint(self, S):
         """S (2l [+1], l, l) from crb200_peg_precision_bwd -> gG (l, l) real.  T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V for all l
@@ -176,11 +175,12 @@ _consts_cache = {}
 def _consts_for(G, dev):
     """The eigendecomposition is redone only when G changes: the key is G's CONTENT (l x l numbers; a model rebuilds the
     tensor from its parameters on every call, so identity or version counters say nothing)."""
-    key = (G.detach().to("cpu", torch.float64).numpy().tobytes(), tuple(G.shape), str(dev))
+    G_host = G.detach().to("cpu", torch.float64)
+    key = (G_host.numpy().tobytes(), tuple(G.shape), str(dev))
     hit = _consts_cache.get("last")
     if hit is not None and hit[0] == key:
         return hit[1]
-    c = _EigConsts(G, dev)
+    c = _EigConsts(G, dev, G_host)
     _consts_cache["last"] = (key, c)
     return c
 
