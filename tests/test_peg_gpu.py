@@ -123,3 +123,31 @@ def test_builder_logdet_is_the_prior_logdet_of_the_reference(l, dtype, tol_f, to
     Gd = G.clone().requires_grad_(True)
     peg_precision(gaps.to(dtype).cuda(), Gd, None, logdet=True)[2].sum().backward()
     assert_close(Gd.grad, Gr.grad, tol_g, "gG from logdet alone")
+
+
+@pytest.mark.parametrize("l,dtype,tol_f,tol_g", [(8, torch.float32, 2e-5, 1e-4), (8, torch.float64, 1e-11, 1e-9), (5, torch.float64, 1e-11, 1e-9),
+                                                (3, torch.float32, 2e-5, 1e-4)])
+def test_builder_many_tiles_per_persistent_cta(l, dtype, tol_f, tol_g):
+    """The backward kernel runs persistent CTAs whose warps reuse their shared-memory records and weight tables round after round
+    (next tile prefetched under the accumulation phase): enough gaps for several rounds per CTA, ragged last tiles, against the
+    same formulas in fp64 torch ops on the device."""
+    from cyclic_gps.peg import peg_precision, peg_precision_torch
+    B, n = 96, 2203                                     # 69 tiles per series, 6624 tiles: > 7 rounds of 296 CTAs x 3 warps
+    G, shift = _model_G(l, 5 + l)
+    gen = torch.Generator(device="cuda").manual_seed(l)
+    gaps = (-torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64, device="cuda")) + 0.02)
+    cR = torch.randn((B, n, l, l), generator=gen, dtype=torch.float64, device="cuda")
+    cR = cR + cR.transpose(-1, -2)
+    cO = torch.randn((B, n - 1, l, l), generator=gen, dtype=torch.float64, device="cuda")
+    cl = torch.randn(B, generator=gen, dtype=torch.float64, device="cuda")
+    Gr, sr = G.cuda().requires_grad_(True), shift.cuda().requires_grad_(True)
+    R0, O0, ld0 = peg_precision_torch(gaps.to(dtype).double(), Gr, sr, logdet=True)
+    ((R0 * cR).sum() + (O0 * cO).sum() + (ld0 * cl).sum()).backward()
+    Gd, sd = G.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+    R1, O1, ld1 = peg_precision(gaps.to(dtype), Gd, sd, logdet=True)
+    assert_close(R1, R0, tol_f, "Rs")
+    assert_close(O1, O0, tol_f, "Os")
+    assert_close(ld1, ld0, tol_f, "logdet")
+    ((R1 * cR.to(dtype)).sum() + (O1 * cO.to(dtype)).sum() + (ld1 * cl).sum()).backward()
+    assert_close(sd.grad, sr.grad, tol_g, "g shift")
+    assert_close(Gd.grad, Gr.grad, tol_g, "gG")

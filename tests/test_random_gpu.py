@@ -26,6 +26,11 @@ def _cases():
     cases.append((700, 8, torch.float32, 300, 100))      # more than two series per SM: no fused tail
     cases.append((700, 8, torch.float32, 290, 101))      # fused tail with an almost full wave of CTAs
     cases.append((333, 3, torch.float64, 301, 102))
+    # large batches: the single-tile deep levels run as ONE launch of single-warp CTAs (more CTAs than one wave holds)
+    cases.append((2049, 4, torch.float32, 310, 103))
+    cases.append((129, 5, torch.float64, 400, 104))
+    cases.append((1000, 2, torch.float32, 1300, 105))
+    cases.append((63, 8, torch.float32, 1500, 106))
     return cases
 
 
