@@ -100,6 +100,11 @@ def build(force=False, jobs=None, verbose=False, only=None):
     units.append((abi_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_abi.cu"), "-o", abi_obj]))
     peg_obj = os.path.join(BUILD, "cr_peg_inst.o")          # precision-block builder (cr_peg.cuh), ell = 1..8, both dtypes
     units.append((peg_obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cr_peg_inst.cu"), "-o", peg_obj]))
+    for tn, ty in (("f32", "float"), ("f64", "double")):      # warp-per-gap builder (cr_pegw.cuh), ell = 9..32
+        for lo, hi in RANGES[2:]:
+            obj = os.path.join(BUILD, f"pegw_{tn}_{lo}_{hi}.o")
+            units.append((obj, [nvcc] + NVCC_FLAGS + [f"-DCRB_T={ty}", f"-DCRB_TN={tn}", f"-DCRB_LO={lo}", f"-DCRB_HI={hi}",
+                                                      "-c", os.path.join(CSRC, "cr_pegw_inst.cu"), "-o", obj]))
     jobs = jobs or min(len(units), os.cpu_count() or 4)
     # longest units (large ell) first
     units.sort(key=lambda u: -int(u[0].rsplit("_", 1)[-1].split(".")[0]) if "inst_" in u[0] else 0)

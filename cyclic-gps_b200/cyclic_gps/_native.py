@@ -92,10 +92,10 @@ class PegBwdArgs(C.Structure):
     _fields_ = [("batch", _i), ("n", _i), ("gaps", _vp), ("stride_gaps", _ll),
                 ("lam_re", _vp), ("lam_im", _vp), ("M_re", _vp), ("M_im", _vp),
                 ("O", _vp), ("strideO", _ll), ("gR", _vp), ("gO", _vp), ("stride_gR", _ll), ("stride_gO", _ll), ("S", _vp),
-                ("nterms", _i), ("g_logdet", _vp)]
+                ("nterms", _i), ("g_logdet", _vp), ("gA", _vp)]
 
 
-EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
+EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_peg_sum_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
            "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd", "crb200_sweep_halfsolve",
            "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_launch_count")
 
@@ -143,6 +143,8 @@ def load():
         lib.crb200_peg_precision_bwd.argtypes = [_i, _i, C.POINTER(PegBwdArgs), _vp]
         lib.crb200_peg_max_ell.restype = _i
         lib.crb200_peg_max_ell.argtypes = []
+        lib.crb200_peg_sum_max_ell.restype = _i
+        lib.crb200_peg_sum_max_ell.argtypes = []
         for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
             getattr(lib, name).restype = _i
             getattr(lib, name).argtypes = [_i, _i]
@@ -260,6 +262,10 @@ def peg_bwd(dtype: torch.dtype, ell: int, **fields):
 
 def peg_max_ell() -> int:
     return int(load().crb200_peg_max_ell())
+
+
+def peg_sum_max_ell() -> int:
+    return int(load().crb200_peg_sum_max_ell())
 
 
 def launch_count() -> int:

@@ -9,8 +9,9 @@ written once, in the layout the level-0 CR kernel reads; with ``ts`` as the only
 ships 4 bytes per row to the GPU instead of (2 l^2 + l) elements.
 
 G is eigendecomposed once per call on the host (l x l, as the reference's ``compute_eG`` does, model_utils.py:12-29).
-Block sizes above ``crb200_peg_max_ell()`` (8), an ill-conditioned eigenbasis or CPU-only use fall back to the same
-formulas in torch ops (``peg_precision_torch``), which is also the oracle of the tests."""
+Ranks up to 8 run on thread-per-gap kernels (cr_peg.cuh), ranks 9..32 on warp-per-gap kernels whose block algebra runs on
+the FP64 tensor path (cr_pegw.cuh).  An ill-conditioned eigenbasis or CPU-only use fall back to the same formulas in torch ops
+(``peg_precision_torch``), which is also the oracle of the tests."""
 import numpy as np
 import torch
 
@@ -103,6 +104,24 @@ class _EigConsts:
             self.re_idx, self.im_idx, self.diag = ipack[0], ipack[1], ipack[2, 0]
             self.im_sign = ipack[2, 1].to(torch.float64).view(1, l, 1, 1)
 
+    def weight_rows(self, gaps, dtype):
+        """E (2l, gaps): for every eigenvalue m < nterms the rows Re e^{c lam_m}, c Re e^{c lam_m} [, Im .., c Im ..], c = -gap / 2
+        rounded like the kernels do (storage type first), in the row order of `rows`."""
+        dev = gaps.device
+        if getattr(self, "_erow", None) is None:
+            part, which = np.zeros(2 * self.V.shape[0], dtype=np.int64), np.zeros(2 * self.V.shape[0], dtype=np.int64)
+            for m, q in enumerate(self.rows):
+                for k, r in enumerate(q):
+                    if r >= 0:
+                        part[r], which[r] = k, m
+            self._erow = torch.from_numpy(np.stack([part, which])).to(dev)
+        l, nt = self.V.shape[0], self.nterms
+        c = (gaps.to(dtype) * -0.5).to(torch.float64).reshape(-1)
+        lam = torch.complex(self.buf[:nt], self.buf[l:l + nt])
+        ec = torch.exp(c.unsqueeze(1) * lam.unsqueeze(0))                             # (gaps, nterms)
+        parts = torch.stack([ec.real, c.unsqueeze(1) * ec.real, ec.imag, c.unsqueeze(1) * ec.imag])
+        return parts[self._erow[0], :, self._erow[1]]
+
     def finish_expm_adjoint(self, S):
         """S (2l [+1], l, l) from crb200_peg_precision_bwd -> gG (l, l) real.  T_m = V^{-1} (sum_g e^{c lam_m} gA_g^T) V for all l
         eigenvalues (conjugates by conjugation), Z_jk = (T_j - T_k)[k, j] / (lam_j - lam_k), the c-weighted sums on the
@@ -153,14 +172,21 @@ class _PegFn(torch.autograd.Function):
         gG = gshift = None
         if ctx.needs_input_grad[1]:
             S = torch.zeros((2 * l + 1, l, l), dtype=torch.float64, device=dev)
+            wide = l > _native.peg_sum_max_ell()
             if n > 1:
                 gRc = _engine._rows_contiguous(gR.to(dtype))
                 gOc = _engine._rows_contiguous(gO.to(dtype))
                 gl = gld.to(torch.float64).contiguous() if ctx.want_logdet else None
+                gA = torch.empty((B * (n - 1), l * l), dtype=torch.float64, device=dev) if wide else None
                 _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
                                 lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im,
                                 O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), S=S,
-                                nterms=c.nterms, g_logdet=gl)
+                                nterms=c.nterms, g_logdet=gl, gA=gA)
+                if wide:
+                    # warp-per-gap kernels (ranks 9..32) return gA_g per gap: the weighted sums over the gaps are one fp64 GEMM,
+                    # (2l x gaps) x (gaps x l^2), with the same weights E the thread-per-gap kernel forms (include/crb200.h)
+                    S[:2 * l] = (c.weight_rows(gaps, dtype) @ gA).view(2 * l, l, l).transpose(1, 2)
+                    S[2 * l] = gRc.sum(dim=(0, 1), dtype=torch.float64)
             gG = c.finish_expm_adjoint(S).to(*ctx.G_meta)
             if n > 1 and ctx.shift_meta is not None and ctx.needs_input_grad[2]:
                 gshift = S[2 * l].to(*ctx.shift_meta)              # the kernel sums the gR rows it stages anyway

@@ -194,11 +194,15 @@ typedef struct crb200_peg_bwd_args {
   double* S;                                           /* (2*ell + 1, ell*ell) doubles, ACCUMULATED into: see above; the last row is sum_i gR_i */
   int nterms;                                          /* as in crb200_peg_fwd_args */
   const double* g_logdet;                              /* (batch) or NULL: cotangent of the forward's logdet output (adds 2 g B_g to gA_g) */
+  double* gA;                                          /* ell > crb200_peg_sum_max_ell() only: (batch, n-1, ell, ell) doubles, receives gA_g per gap
+                                                          (row-major); the weighted sums over the gaps are then the caller's GEMM and S is not touched */
 } crb200_peg_bwd_args;
 
 int crb200_peg_precision_fwd(int dtype, int ell, const crb200_peg_fwd_args* args, void* stream);
 int crb200_peg_precision_bwd(int dtype, int ell, const crb200_peg_bwd_args* args, void* stream);
-int crb200_peg_max_ell(void);                          /* largest ell the builder kernels exist for (larger: host falls back to torch ops) */
+int crb200_peg_max_ell(void);                          /* largest ell the builder kernels exist for (32) */
+int crb200_peg_sum_max_ell(void);                      /* largest ell for which the backward entry also sums over the gaps (8: thread-per-gap kernels);
+                                                          above it the warp-per-gap kernels return gA per gap (field gA) */
 
 int crb200_version(void);
 int crb200_max_ell(void);

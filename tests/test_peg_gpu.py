@@ -22,7 +22,7 @@ def _model_G(l, seed, noise=1.0):
 
 
 @pytest.mark.parametrize("dtype,tol_f,tol_g", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 1e-4)])
-@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32])     # <= 8: thread per gap; 9..32: warp per gap (DMMA)
 def test_builder_forward_and_backward_vs_torch_autograd(l, dtype, tol_f, tol_g):
     from cyclic_gps.peg import peg_precision, peg_precision_torch
     for (B, n, seed) in ((1, 2, 1), (3, 33, 2), (2, 100, 3), (5, 31, 4), (1, 1, 5)):
@@ -77,7 +77,7 @@ def test_degenerate_eigenvalues_and_regular_spacing():
 
 
 @pytest.mark.parametrize("dtype,tol_f,tol_g", [(torch.float64, 1e-11, 1e-9), (torch.float32, 2e-5, 1e-4)])
-@pytest.mark.parametrize("l", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("l", [1, 2, 3, 5, 8, 10, 16, 32])
 def test_builder_logdet_is_the_prior_logdet_of_the_reference(l, dtype, tol_f, tol_g):
     """logdet=True: log det of the unshifted block-tridiagonal precision as a by-product of the builder.  The
     reference obtains the same number from a second cyclic reduction, det(decompose(Sigma^{-1})) (models.py:349-353): compared
@@ -126,13 +126,13 @@ def test_builder_logdet_is_the_prior_logdet_of_the_reference(l, dtype, tol_f, to
 
 
 @pytest.mark.parametrize("l,dtype,tol_f,tol_g", [(8, torch.float32, 2e-5, 1e-4), (8, torch.float64, 1e-11, 1e-9), (5, torch.float64, 1e-11, 1e-9),
-                                                (3, torch.float32, 2e-5, 1e-4)])
+                                                (3, torch.float32, 2e-5, 1e-4), (16, torch.float64, 1e-11, 1e-9), (12, torch.float32, 2e-5, 1e-4)])
 def test_builder_many_tiles_per_persistent_cta(l, dtype, tol_f, tol_g):
     """The backward kernel runs persistent CTAs whose warps reuse their shared-memory records and weight tables round after round
     (next tile prefetched under the accumulation phase): enough gaps for several rounds per CTA, ragged last tiles, against the
     same formulas in fp64 torch ops on the device."""
     from cyclic_gps.peg import peg_precision, peg_precision_torch
-    B, n = 96, 2203                                     # 69 tiles per series, 6624 tiles: > 7 rounds of 296 CTAs x 3 warps
+    B, n = (96, 2203) if l <= 8 else (24, 1201)         # 69 tiles per series, 6624 tiles: > 7 rounds of 296 CTAs x 3 warps (warp per gap: 28800 gaps)
     G, shift = _model_G(l, 5 + l)
     gen = torch.Generator(device="cuda").manual_seed(l)
     gaps = (-torch.log(torch.rand((B, n - 1), generator=gen, dtype=torch.float64, device="cuda")) + 0.02)
