@@ -15,6 +15,7 @@ One JSON line is printed by rank 0.  Besides the headline (`value`, weak scaling
                NCCL all-gather (cyclic_gps.distributed), with its own clocks record and a parity block (chunked on N
                ranks vs the unchunked single sweep at n = 4e6, and the residual of J w = x at the full size)."""
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -63,6 +64,19 @@ def peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def quiet_gc():
+    """Collect now and keep the cyclic collector off during a timed loop (as timeit does); returns the previous state."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    return was
+
+
+def restore_gc(was):
+    if was:
+        gc.enable()
 
 
 class ClockSampler:
@@ -388,11 +402,13 @@ def run_long(args, rk, standalone):
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lc0 = _native.launch_count()
+    gc_was = quiet_gc()               # a collector pause on ONE rank stalls all of them at the all-gather (the step is ~3 ms of kernels at 8 GPUs)
     e0.record()
     for _ in range(args.steps):
         ll = step().detach()
     e1.record()
     rk.sync()
+    restore_gc(gc_was)
     ms = e0.elapsed_time(e1)
     timed_launches = _native.launch_count() - lc0       # kernels of libcrb200 launched inside the timed region
     trace.enabled = True
@@ -549,11 +565,13 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
         fn(); fn()
         rk.sync()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc_was = quiet_gc()
         a0.record()
         for _ in range(k):
             fn()
         a1.record()
         rk.sync()
+        restore_gc(gc_was)
         return rk.max_over_ranks(a0.elapsed_time(a1) / k)
 
     k2 = max(3, min(args.steps, 5))
@@ -621,11 +639,13 @@ def time_batch(rk, cr, tensors, steps, warmup):
     rk.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lc0 = _native.launch_count()
+    gc_was = quiet_gc()
     e0.record()
     for _ in range(steps):
         total += step().detach()
     e1.record()
     rk.sync()
+    restore_gc(gc_was)
     ms = rk.max_over_ranks(e0.elapsed_time(e1))
     return ms, step, float(total) / max(steps, 1), _native.launch_count() - lc0
 
