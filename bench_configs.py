@@ -170,15 +170,47 @@ def cfg3(reps):
         Kr, Ko = model._precision_blocks(tsg, shift_g)
         vg = model.compute_v(xsg)
     graphed = GraphedMahalAndDet(Kr, Ko, vg)
+    from cyclic_gps.graphs import GraphedLogLikelihood
+    runner = GraphedLogLikelihood(model, tsg, xsg)
+
+    def graphed_step(move=False):
+        model.zero_grad(set_to_none=True)
+        ll = runner()
+        (-ll / n).backward()
+        if move:        # an optimiser step changes G: the eigen-constants are recomputed on the host and refreshed in place
+            with torch.no_grad():
+                model.R_params.add_(1e-6)
+        return ll
+
+    # the same runner with the (73-number) model on the HOST: the l x l / d x d parameter algebra then costs no launches at all
+    hmodel = LEGFamily(rank=rank, obs_dim=1, train=True, data_type=torch.float64)
+    hmodel.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    hrunner = GraphedLogLikelihood(hmodel, tsg, xsg)
+
+    def graphed_step_host_model():
+        hmodel.zero_grad(set_to_none=True)
+        ll = hrunner()
+        (-ll / n).backward()
+        with torch.no_grad():
+            hmodel.R_params.add_(1e-6)
+        return ll
+
+    ll_g = graphed_step()
+    g_graphed = {k: getattr(model, k).grad.clone() for k in ("N_params", "R_params", "Lambda_params", "B")}
     ll, ll_o = step(), ref_step()
     g_err = max(rel(getattr(model, k).grad, getattr(ref, k).grad) for k in ("N_params", "R_params", "Lambda_params", "B"))
+    gg_err = max(rel(g_graphed[k], getattr(ref, k).grad) for k in g_graphed)
     (mean, cov), (mean_o, (sd, so)) = posterior(), ref_posterior()
     return {"config": "cfg3: CO2-shaped, n=502 (240-unit gap), l=16, fp64, obs_dim=1",
             "gpu_train_step_ms": gpu_time(step, reps), "gpu_posterior_ms": gpu_time(posterior, reps),
             "gpu_cr_loglik_grad_cuda_graph_ms": gpu_time(lambda: graphed(Kr, Ko, vg), reps),
+            "gpu_train_step_cuda_graph_ms": gpu_time(graphed_step, reps),
+            "gpu_train_step_cuda_graph_moving_parameters_ms": gpu_time(lambda: graphed_step(True), reps),
+            "gpu_train_step_cuda_graph_host_model_ms": gpu_time(graphed_step_host_model, reps),
             "reference_cpu_train_step_ms": cpu_time(ref_step), "reference_cpu_posterior_ms": cpu_time(ref_posterior),
             "cores": torch.get_num_threads(),
-            "parity": {"loglik": rel(ll, ll_o), "param_grads": g_err, "posterior_mean": rel(mean, mean_o),
+            "parity": {"loglik": rel(ll, ll_o), "param_grads": g_err, "graphed_loglik": rel(ll_g, ll_o), "graphed_param_grads": gg_err,
+                       "posterior_mean": rel(mean, mean_o),
                        "posterior_cov_diag": rel(cov["Rs"], sd), "posterior_cov_off": rel(cov["Os"], so)}}
 
 

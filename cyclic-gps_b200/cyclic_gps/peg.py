@@ -44,13 +44,43 @@ class _EigConsts:
     """Everything the kernels need about G, as ONE device array of doubles (+ complex V, V^{-1} on the device)."""
 
     def __init__(self, G, dev, G_host=None):
-        # plain numpy on the host: for l x l matrices the per-call overhead of tensor ops is what this constructor costs
-        l = G.shape[0]
         Gc = (G_host if G_host is not None else G.detach().to("cpu", torch.float64)).numpy()
+        h = self._host(Gc)
+        l = Gc.shape[0]
+        self.cond, self.nterms, self.partner, self.rows, self.folded = h["cond"], h["nterms"], h["partner"], h["rows"], h["folded"]
+        # three host -> device copies in all (small problems are bound by such calls): doubles, one complex pack, one index pack
+        self.buf = torch.from_numpy(h["flat"]).to(dev)
+        base = self.buf.data_ptr()
+        self.lam_re, self.lam_im, self.M_re, self.M_im = base, base + 8 * l, base + 16 * l, base + 16 * l + 8 * l * l * l
+        self.cpack = torch.from_numpy(h["cpack"]).to(dev)
+        self.V, self.Vinv, self.invdl = self.cpack[0], self.cpack[1], self.cpack[2]
+        self.deg = self.invdl == 0                                  # 1 / (lam_j - lam_k) is stored as 0 exactly where the pair is degenerate
+        if self.folded:
+            ipack = torch.from_numpy(h["ipack"]).to(dev)
+            self.re_idx, self.im_idx, self.diag = ipack[0], ipack[1], ipack[2, 0]
+            self.im_sign = ipack[2, 1].to(torch.float64).view(1, l, 1, 1)
+
+    def refresh(self, G_host):
+        """New values of G into the SAME device arrays (a captured CUDA graph holds their addresses).  Returns False -- nothing
+        copied -- when the structure of the spectrum (number of complex pairs / real eigenvalues, degenerate pairs handled by the
+        index packs) has changed: the caller then has to build new constants and capture again."""
+        h = self._host(G_host.numpy())
+        if (h["nterms"], h["rows"], h["folded"], h["partner"]) != (self.nterms, self.rows, self.folded, self.partner):
+            return False
+        self.cond = h["cond"]
+        self.buf.copy_(torch.from_numpy(h["flat"]), non_blocking=True)
+        self.cpack.copy_(torch.from_numpy(h["cpack"]), non_blocking=True)
+        self.deg.copy_(self.invdl == 0)
+        return True
+
+    @staticmethod
+    def _host(Gc):
+        # plain numpy on the host: for l x l matrices the per-call overhead of tensor ops is what this step costs
+        l = Gc.shape[0]
         lam, V = np.linalg.eig(Gc)
         lam, V = lam.astype(np.complex128), V.astype(np.complex128)
         sv = np.linalg.svd(V, compute_uv=False)
-        self.cond = float(sv[0] / sv[-1]) if sv[-1] > 0 else float("inf")
+        cond = float(sv[0] / sv[-1]) if sv[-1] > 0 else float("inf")
         # Order the spectrum as [eigenvalues with Im > 0 | real eigenvalues | conjugates of the first group] and make the
         # conjugate columns of V exact conjugates (G is real): the expansion of exp(cG) - I then only needs the first
         # `nterms` terms (complex ones doubled), and the kernel only accumulates the sums of one member of every pair.
@@ -65,12 +95,11 @@ class _EigConsts:
                 ph = Vr[np.abs(Vr).argmax(axis=0), np.arange(nreal)]
                 Vr = (Vr * (ph.conj() / np.abs(ph))).real.astype(np.complex128)
             V = np.concatenate([V[:, pos], Vr, V[:, pos].conj()], axis=1)
-            self.nterms = nt = npos + nreal
-            self.partner = list(range(nt, l)) + list(range(npos, nt)) + list(range(npos))
+            nt = npos + nreal
+            partner = list(range(nt, l)) + list(range(npos, nt)) + list(range(npos))
             weights = np.concatenate([np.full(npos, 2.0), np.ones(nreal)])
         else:                                           # (spectrum not closed under conjugation: cannot happen for a real G)
-            self.nterms = nt = l
-            self.partner, weights = None, np.ones(l)
+            nt, partner, weights = l, None, np.ones(l)
         Vinv = np.linalg.inv(V)
         M = (V.T[:, :, None] * Vinv[:, None, :]).reshape(l, l * l)          # M_k = V[:, k] V^{-1}[k, :]
         lam_t = np.concatenate([lam[:nt], np.zeros(l - nt, dtype=np.complex128)])
@@ -78,31 +107,24 @@ class _EigConsts:
         dl = lam[:, None] - lam[None, :]
         deg = np.abs(dl) <= 1e-9 * max(float(np.abs(lam).max()), 1e-300)
         invdl = np.where(deg, 0.0, 1.0 / np.where(deg, 1.0, dl))
-        flat = np.concatenate([lam_t.real, lam_t.imag, M_t.real.reshape(-1), M_t.imag.reshape(-1)])
-        self.buf = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
-        base = self.buf.data_ptr()
-        self.lam_re, self.lam_im, self.M_re, self.M_im = base, base + 8 * l, base + 16 * l, base + 16 * l + 8 * l * l * l
+        flat = np.ascontiguousarray(np.concatenate([lam_t.real, lam_t.imag, M_t.real.reshape(-1), M_t.imag.reshape(-1)]))
         # host side of the backward pass (finish_expm_adjoint): which rows of the kernel's S belong to which eigenvalue
         cplx = lam_t[:nt].imag != 0.0
         r0 = np.concatenate([[0], np.cumsum(np.where(cplx, 4, 2))])
-        self.rows = [(int(r0[m]), int(r0[m]) + 1, int(r0[m]) + 2 if cplx[m] else -1, int(r0[m]) + 3 if cplx[m] else -1) for m in range(nt)]
-        self.folded = self.partner is not None and int(r0[-1]) == 2 * l
-        # three host -> device copies in all (small problems are bound by such calls): the doubles above, one complex pack, one index pack
-        cpack = torch.from_numpy(np.stack([V, Vinv, invdl.astype(np.complex128)])).to(dev)
-        self.V, self.Vinv, self.invdl = cpack[0], cpack[1], cpack[2]
-        self.deg = self.invdl == 0                                  # 1 / (lam_j - lam_k) is stored as 0 exactly where the pair is degenerate
-        if self.folded:
+        rows = [(int(r0[m]), int(r0[m]) + 1, int(r0[m]) + 2 if cplx[m] else -1, int(r0[m]) + 3 if cplx[m] else -1) for m in range(nt)]
+        folded = partner is not None and int(r0[-1]) == 2 * l
+        out = {"cond": cond, "nterms": nt, "partner": partner, "rows": rows, "folded": folded, "flat": flat,
+               "cpack": np.stack([V, Vinv, invdl.astype(np.complex128)]), "ipack": None}
+        if folded:
             # index form of `rows` for the device: row 2l of the (zero-extended) S stands for "no imaginary part"; eigenvalue m >= nterms
             # is the conjugate of its partner
-            src = np.array(list(range(nt)) + self.partner[nt:], dtype=np.int64)
+            src = np.array(list(range(nt)) + partner[nt:], dtype=np.int64)
             base_r = r0[:-1][src]
             im0 = np.where(cplx[src], base_r + 2, 2 * l)
             im1 = np.where(cplx[src], base_r + 3, 2 * l)
-            ipack = np.stack([np.stack([base_r, base_r + 1]), np.stack([im0, im1]),
-                              np.stack([np.arange(l), np.concatenate([np.ones(nt), -np.ones(l - nt)]).astype(np.int64)])]).astype(np.int64)
-            ipack = torch.from_numpy(ipack).to(dev)
-            self.re_idx, self.im_idx, self.diag = ipack[0], ipack[1], ipack[2, 0]
-            self.im_sign = ipack[2, 1].to(torch.float64).view(1, l, 1, 1)
+            out["ipack"] = np.stack([np.stack([base_r, base_r + 1]), np.stack([im0, im1]),
+                                     np.stack([np.arange(l), np.concatenate([np.ones(nt), -np.ones(l - nt)]).astype(np.int64)])]).astype(np.int64)
+        return out
 
     def weight_rows(self, gaps, dtype):
         """E (2l, gaps): for every eigenvalue m < nterms the rows Re e^{c lam_m}, c Re e^{c lam_m} [, Im .., c Im ..], c = -gap / 2
@@ -138,21 +160,53 @@ class _EigConsts:
         return (self.Vinv.transpose(0, 1) @ Z @ self.V.transpose(0, 1)).real
 
 
+def builder_forward(c, gaps, shift64, dtype, want_logdet=True):
+    """One launch of crb200_peg_precision_fwd: gaps (B, n-1) -> R, O, log det of the unshifted precision (B,) float64, info."""
+    B, nm1 = gaps.shape
+    n, l, dev = nm1 + 1, c.V.shape[0], gaps.device
+    R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
+    O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    ld = torch.zeros(B, dtype=torch.float64, device=dev)
+    _native.peg_fwd(dtype, l, batch=B, n=n, gaps=gaps if nm1 > 0 else None, stride_gaps=gaps.stride(0) if nm1 > 0 else 0,
+                    lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im, shift=shift64,
+                    R=R, O=O if nm1 > 0 else None, strideR=n * l * l, strideO=nm1 * l * l, info=info, nterms=c.nterms,
+                    logdet=ld if want_logdet else None)
+    return R, O, ld, info
+
+
+def builder_backward(c, gaps, O, gR, gO, g_logdet, dtype):
+    """crb200_peg_precision_bwd + the host finish: cotangents of (R, O, logdet) -> (gG (l, l) float64, sum of the gR rows (l, l) float64)."""
+    B, nm1 = gaps.shape
+    n, l, dev = nm1 + 1, c.V.shape[0], gaps.device
+    S = torch.zeros((2 * l + 1, l, l), dtype=torch.float64, device=dev)
+    gRc = _engine._rows_contiguous(gR.to(dtype))
+    if n > 1:
+        wide = l > _native.peg_sum_max_ell()
+        gOc = _engine._rows_contiguous(gO.to(dtype))
+        gA = torch.empty((B * (n - 1), l * l), dtype=torch.float64, device=dev) if wide else None
+        _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
+                        lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im,
+                        O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), S=S,
+                        nterms=c.nterms, g_logdet=g_logdet, gA=gA)
+        if wide:
+            # warp-per-gap kernels (ranks 9..32) return gA_g per gap: the weighted sums over the gaps are one fp64 GEMM,
+            # (2l x gaps) x (gaps x l^2), with the same weights E the thread-per-gap kernel forms (include/crb200.h)
+            S[:2 * l] = (c.weight_rows(gaps, dtype) @ gA).view(2 * l, l, l).transpose(1, 2)
+            S[2 * l] = gRc.sum(dim=(0, 1), dtype=torch.float64)
+    else:
+        S[2 * l] = gRc.sum(dim=(0, 1), dtype=torch.float64)
+    return c.finish_expm_adjoint(S), S[2 * l]
+
+
 class _PegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gaps, G, shift, consts, want_logdet):
         B, nm1 = gaps.shape
-        n, l, dtype, dev = nm1 + 1, G.shape[0], gaps.dtype, gaps.device
-        R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
-        O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
-        info = torch.zeros(1, dtype=torch.int32, device=dev)
-        ld = torch.zeros(B, dtype=torch.float64, device=dev)
+        dtype, dev = gaps.dtype, gaps.device
         sh = shift.detach().to(dev, torch.float64).contiguous() if shift is not None else None
-        _native.peg_fwd(dtype, l, batch=B, n=n, gaps=gaps if nm1 > 0 else None, stride_gaps=gaps.stride(0) if nm1 > 0 else 0,
-                        lam_re=consts.lam_re, lam_im=consts.lam_im, M_re=consts.M_re, M_im=consts.M_im, shift=sh,
-                        R=R, O=O if nm1 > 0 else None, strideR=n * l * l, strideO=nm1 * l * l, info=info, nterms=consts.nterms,
-                        logdet=ld if want_logdet else None)
-        ctx.consts, ctx.meta = consts, (B, n, l, dtype)
+        R, O, ld, info = builder_forward(consts, gaps, sh, dtype, want_logdet)
+        ctx.consts, ctx.dtype = consts, dtype
         ctx.save_for_backward(gaps, O)
         ctx.G_meta = (G.device, G.dtype)
         ctx.shift_meta = (shift.device, shift.dtype) if shift is not None else None
@@ -166,30 +220,13 @@ class _PegFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gR, gO, gld):
         gaps, O = ctx.saved_tensors
-        B, n, l, dtype = ctx.meta
-        c = ctx.consts
-        dev = gaps.device
         gG = gshift = None
         if ctx.needs_input_grad[1]:
-            S = torch.zeros((2 * l + 1, l, l), dtype=torch.float64, device=dev)
-            wide = l > _native.peg_sum_max_ell()
-            if n > 1:
-                gRc = _engine._rows_contiguous(gR.to(dtype))
-                gOc = _engine._rows_contiguous(gO.to(dtype))
-                gl = gld.to(torch.float64).contiguous() if ctx.want_logdet else None
-                gA = torch.empty((B * (n - 1), l * l), dtype=torch.float64, device=dev) if wide else None
-                _native.peg_bwd(dtype, l, batch=B, n=n, gaps=gaps, stride_gaps=gaps.stride(0),
-                                lam_re=c.lam_re, lam_im=c.lam_im, M_re=c.M_re, M_im=c.M_im,
-                                O=O, strideO=O.stride(0), gR=gRc, gO=gOc, stride_gR=gRc.stride(0), stride_gO=gOc.stride(0), S=S,
-                                nterms=c.nterms, g_logdet=gl, gA=gA)
-                if wide:
-                    # warp-per-gap kernels (ranks 9..32) return gA_g per gap: the weighted sums over the gaps are one fp64 GEMM,
-                    # (2l x gaps) x (gaps x l^2), with the same weights E the thread-per-gap kernel forms (include/crb200.h)
-                    S[:2 * l] = (c.weight_rows(gaps, dtype) @ gA).view(2 * l, l, l).transpose(1, 2)
-                    S[2 * l] = gRc.sum(dim=(0, 1), dtype=torch.float64)
-            gG = c.finish_expm_adjoint(S).to(*ctx.G_meta)
-            if n > 1 and ctx.shift_meta is not None and ctx.needs_input_grad[2]:
-                gshift = S[2 * l].to(*ctx.shift_meta)              # the kernel sums the gR rows it stages anyway
+            gl = gld.to(torch.float64).contiguous() if ctx.want_logdet else None
+            gG, gsum = builder_backward(ctx.consts, gaps, O, gR, gO, gl, ctx.dtype)
+            gG = gG.to(*ctx.G_meta)
+            if ctx.shift_meta is not None and ctx.needs_input_grad[2]:
+                gshift = gsum.to(*ctx.shift_meta)                  # the kernel sums the gR rows it stages anyway
         if gshift is None and ctx.shift_meta is not None and ctx.needs_input_grad[2]:
             gshift = gR.sum(dim=(0, 1), dtype=torch.float64).to(*ctx.shift_meta)
         return None, gG, gshift, None, None

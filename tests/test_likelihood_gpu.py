@@ -166,3 +166,36 @@ def test_predictions_match_the_reference(golden):
             ref = torch.from_numpy(g[p + key])
             err = float((ours.cpu() - ref).abs().max() / ref.abs().max())
             assert err < 1e-8, (p, key, err)
+
+
+@pytest.mark.parametrize("rank,d,B,n,dtype,tol_v,tol_g,on_gpu", [(5, 2, 1, 120, torch.float64, 1e-10, 1e-8, False), (8, 1, 3, 257, torch.float32, 1e-4, 2e-3, True),
+                                                                 (16, 1, 1, 502, torch.float64, 1e-10, 1e-8, True), (3, 1, 2, 1000, torch.float64, 1e-10, 1e-8, True)])
+def test_graphed_log_likelihood_matches_eager(rank, d, B, n, dtype, tol_v, tol_g, on_gpu):
+    """cyclic_gps.graphs.GraphedLogLikelihood: one CUDA-graph replay per evaluation gives the value and the parameter gradients of
+    the eager LEGFamily.log_likelihood(...).sum(), also after the parameters have moved (the constants of G are refreshed in place)."""
+    from cyclic_gps.graphs import GraphedLogLikelihood
+    from cyclic_gps.models import LEGFamily
+    torch.manual_seed(rank + n)
+    gaps = torch.rand((B, n - 1), dtype=torch.float64) + 0.05
+    ts = torch.cat([torch.zeros((B, 1), dtype=torch.float64), torch.cumsum(gaps, 1)], 1)
+    xs = torch.randn((B, n, d), dtype=dtype)
+    model = LEGFamily(rank=rank, obs_dim=d, train=True, data_type=dtype)
+    if on_gpu:
+        model, ts, xs = model.cuda(), ts.cuda(), xs.cuda()
+    runner = GraphedLogLikelihood(model, ts, xs)
+    names = ("N_params", "R_params", "Lambda_params", "B")
+    for it in range(3):
+        model.zero_grad(set_to_none=True)
+        want = model.log_likelihood(ts, xs).sum()
+        (-want / n).backward()
+        gw = [getattr(model, nm).grad.clone() for nm in names]
+        model.zero_grad(set_to_none=True)
+        got = runner()
+        (-got / n).backward()
+        assert_close(got, want, tol_v, f"graphed loglik, step {it}")
+        for nm, g0 in zip(names, gw):
+            assert_close(getattr(model, nm).grad, g0, tol_g, f"graphed grad {nm}, step {it}")
+        with torch.no_grad():                             # move the parameters like an optimizer step would
+            for nm in names:
+                p = getattr(model, nm)
+                p.add_(0.03 * torch.randn(p.shape, dtype=p.dtype, device=p.device, generator=None))

@@ -57,3 +57,34 @@ torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
 st.sort_stats("cumulative").print_stats(45)
+
+# the same step through cyclic_gps.graphs.GraphedLogLikelihood (one CUDA-graph replay for the device part)
+from cyclic_gps.graphs import GraphedLogLikelihood  # noqa: E402
+runner = GraphedLogLikelihood(model, ts, xs)
+
+
+def gstep():
+    model.zero_grad(set_to_none=True)
+    ll = runner()
+    (-ll / n).backward()
+    with torch.no_grad():
+        model.R_params.add_(1e-6)
+    return ll
+
+
+for _ in range(5):
+    gstep()
+torch.cuda.synchronize()
+a.record()
+for _ in range(20):
+    gstep()
+b.record()
+torch.cuda.synchronize()
+print("graphed train step ms (parameters moving)", a.elapsed_time(b) / 20)
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(50):
+    gstep()
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(40)
