@@ -14,6 +14,13 @@
 // the top level); the odd rows (S~_d[e], w~_e) are copied through from shared memory.  A CTA is W warps = W
 // consecutive even nodes; the only data shared between warps are S~_d[e-1] and w~_{e-1}, read from the left
 // neighbour's record after ONE __syncthreads that follows the stage-in (warp 0 stages its own copy).
+//
+// Two warps per node for LP >= 24 (TW = 2).  There a node costs 25-46 KB of shared memory, so with one warp per node an SM holds
+// one warp per sub-partition and DMMA time, the serial triangular inverse, staging latency and stores simply add up (ncu, LP = 32:
+// 29.6k cycles per node of which 13.9k are DMMA).  The products of a node come in independent pairs, so a TEAM of two warps shares it:
+//   warp A: Di, P, Di^T Di, N1, P^T N1, Sigma_{2e+1,2e} and Sigma_{2e,2e} out      warp B: Q, w, N2, Q^T N2^T, Sigma_{2e,2e-1} out, odd rows
+// with five named-barrier hand-overs (Di; P and Q; w and the end of Di; S~_o read before N2 overwrites it; B's part of Sigma_ee through
+// the dead Q slot).  Same shared memory per node, twice the warps per SM.  With TW = 1 one warp runs both roles in the same order.
 #pragma once
 #include "cr_level_bwd.cuh"
 #include "cr_mma_common.cuh"
@@ -30,18 +37,26 @@ struct MmaBwdCfg {
   static constexpr int LEFT = BLK + VEC;                      // record of the left neighbour of warp 0: S~_d[e0-1], w~_{e0-1}
   // warps (= nodes) per CTA, chosen so that TWO CTAs fit on an SM (their load / compute / store phases then overlap; see cr_mma_fwd.cuh)
   static constexpr int W = LP <= 16 ? 8 : (LP <= 24 ? 3 : 2);
+  static constexpr int TW = LP >= 24 ? 2 : 1;                 // warps per node (see the header)
   static constexpr int NT = W;
   static constexpr size_t SMEM = (size_t)(LEFT + W * REC) * sizeof(double);
   static constexpr int MIN_CTAS = (2 * (SMEM + 1024) <= 227 * 1024) ? 2 : 1;
 };
 
 template <typename T, int L>
-__global__ void __launch_bounds__(32 * MmaBwdCfg<T, L>::W, MmaBwdCfg<T, L>::MIN_CTAS)
+__global__ void __launch_bounds__(32 * MmaBwdCfg<T, L>::W * MmaBwdCfg<T, L>::TW, MmaBwdCfg<T, L>::MIN_CTAS)
 cr_mma_bwd_kernel(const LevelBwdArgs a) {
   using C = MmaBwdCfg<T, L>;
-  constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NT = C::NT, NTL = LP / 8, BS = L * L;
+  constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NT = C::NT, NTL = LP / 8, BS = L * L, TW = C::TW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) / TW;               // node of this CTA
+  const int sub = (threadIdx.x >> 5) % TW;                // role inside the node's team
+  const bool roleA = TW == 1 || sub == 0, roleB = TW == 1 || sub == 1;
+  auto team_sync = [&]() {
+    if constexpr (TW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, 64;\n" ::"r"(warp + 1) : "memory");
+  };
   double* base = reinterpret_cast<double*>(smem_raw);
   double* N = base + C::LEFT + (size_t)warp * C::REC;
   double* T0 = N;
@@ -77,10 +92,10 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     gd = a.gd != nullptr ? a.gd[b] : 0.0;
   }
 
-  // ---------------- stage in ----------------
+  // ---------------- stage in (role A: D, F, S~_d and the vectors; role B: G, S~_o and the left neighbour of the CTA) ----------------
   // vectors first (plain loads whose latency is covered by the block copies issued next)
   double x_v = 0.0, wt_v = 0.0, lw_v = 0.0;
-  if (do_w && lane < L) {
+  if (roleA && do_w && lane < L) {
     if (valid) x_v = (double)static_cast<const T*>(a.xk)[((size_t)b * E + e) * L + lane];
     if (has_odd) wt_v = (double)static_cast<const T*>(a.w_in)[((size_t)b * o + e) * L + lane];
     if (warp == 0) {
@@ -89,49 +104,59 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     }
   }
   const bool st3 = do_sigma && has_odd, st4 = do_sigma && has_so, stl = do_sigma && warp == 0 && (e0 >= 1 || halo);
-  if (valid) mma_stage_issue<T, L, LP>(T0, static_cast<const T*>(a.D) + ((size_t)b * E + e) * BS, true, lane, is_aligned16(a.D));
-  else mma_fill_block<LP>(T0, true, lane);
-  if (has_odd) mma_stage_issue<T, L, LP>(T1, static_cast<const T*>(a.F) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.F));
-  else mma_fill_block<LP>(T1, false, lane);
-  if (has_left) {
-    if (e >= 1) mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e - 1)) * BS, false, lane, is_aligned16(a.G));
-    else mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G_halo) + (size_t)b * BS, false, lane, is_aligned16(a.G_halo));
-  } else {
-    mma_fill_block<LP>(T2, false, lane);
+  if (roleA) {
+    if (valid) mma_stage_issue<T, L, LP>(T0, static_cast<const T*>(a.D) + ((size_t)b * E + e) * BS, true, lane, is_aligned16(a.D));
+    else mma_fill_block<LP>(T0, true, lane);
+    if (has_odd) mma_stage_issue<T, L, LP>(T1, static_cast<const T*>(a.F) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.F));
+    else mma_fill_block<LP>(T1, false, lane);
+    if (do_sigma) {
+      if (st3) mma_stage_issue<T, L, LP>(T3, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.Sd_in));
+      else mma_fill_block<LP>(T3, false, lane);
+    }
+    if (lane < LP) {
+      X[lane] = x_v;
+      WT[lane] = wt_v;
+      WV[lane] = 0.0;
+      if (warp == 0) base[BLK + lane] = lw_v;
+    }
   }
-  if (do_sigma) {
-    if (st3) mma_stage_issue<T, L, LP>(T3, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + e) * BS, false, lane, is_aligned16(a.Sd_in));
-    else mma_fill_block<LP>(T3, false, lane);
-    if (st4) {
-      if (e >= 1) mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e - 1)) * BS, false, lane, is_aligned16(a.So_in));
-      else mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, false, lane, is_aligned16(a.So_halo_in));
+  if (roleB) {
+    if (has_left) {
+      if (e >= 1) mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e - 1)) * BS, false, lane, is_aligned16(a.G));
+      else mma_stage_issue<T, L, LP>(T2, static_cast<const T*>(a.G_halo) + (size_t)b * BS, false, lane, is_aligned16(a.G_halo));
     } else {
-      mma_fill_block<LP>(T4, false, lane);
+      mma_fill_block<LP>(T2, false, lane);
     }
-    if (warp == 0) {
-      if (e0 >= 1) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1)) * BS, false, lane, is_aligned16(a.Sd_in));
-      else if (halo) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, false, lane, is_aligned16(a.Sd_halo));
-      else mma_fill_block<LP>(base, false, lane);
+    if (do_sigma) {
+      if (st4) {
+        if (e >= 1) mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_in) + ((size_t)b * (o - 1) + (e - 1)) * BS, false, lane, is_aligned16(a.So_in));
+        else mma_stage_issue<T, L, LP>(T4, static_cast<const T*>(a.So_halo_in) + (size_t)b * BS, false, lane, is_aligned16(a.So_halo_in));
+      } else {
+        mma_fill_block<LP>(T4, false, lane);
+      }
+      if (warp == 0) {
+        if (e0 >= 1) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1)) * BS, false, lane, is_aligned16(a.Sd_in));
+        else if (halo) mma_stage_issue<T, L, LP>(base, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, false, lane, is_aligned16(a.Sd_halo));
+        else mma_fill_block<LP>(base, false, lane);
+      }
     }
-  }
-  if (lane < LP) {
-    X[lane] = x_v;
-    WT[lane] = wt_v;
-    WV[lane] = 0.0;
-    if (warp == 0) base[BLK + lane] = lw_v;
   }
   cp_async_wait_all();
   __syncwarp();
-  if (valid) mma_stage_finish<T, L, LP>(T0, true, lane);
-  if (has_odd) mma_stage_finish<T, L, LP>(T1, false, lane);
-  if (has_left) mma_stage_finish<T, L, LP>(T2, false, lane);
-  if (st3) mma_stage_finish<T, L, LP>(T3, false, lane);
-  if (st4) mma_stage_finish<T, L, LP>(T4, false, lane);
-  if (stl) mma_stage_finish<T, L, LP>(base, false, lane);
-  __syncthreads();                                      // the left neighbour's S~_d and w~ are visible
+  if (roleA) {
+    if (valid) mma_stage_finish<T, L, LP>(T0, true, lane);
+    if (has_odd) mma_stage_finish<T, L, LP>(T1, false, lane);
+    if (st3) mma_stage_finish<T, L, LP>(T3, false, lane);
+  }
+  if (roleB) {
+    if (has_left) mma_stage_finish<T, L, LP>(T2, false, lane);
+    if (st4) mma_stage_finish<T, L, LP>(T4, false, lane);
+    if (stl) mma_stage_finish<T, L, LP>(base, false, lane);
+  }
+  __syncthreads();                                      // everything staged is visible, incl. the left neighbour's S~_d and w~
 
-  // ---------------- Di, P, Q, w ----------------
-  {
+  // ---------------- Di (A), P (A), Q (B) ----------------
+  if (roleA) {
     double invd[LP];
     const int r = lane < LP ? lane : 0;
     const double mine = 1.0 / T0[r * LD + r];
@@ -139,27 +164,27 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     for (int j = 0; j < LP; ++j) invd[j] = __shfl_sync(0xffffffffu, mine, j);
     warp_tri_inverse<LP>(T0, invd, lane);               // T0 = Di
   }
+  team_sync();                                          // (1) Di is ready
   double acc[NTL][NTL][2];
-  if (has_odd) {
+  if (roleA && has_odd) {
     acc_zero<LP>(acc);
     warp_gemm<LP, false, false, K_GE_N, false>(acc, T1, T0, lane);         // P = F Di
     __syncwarp();
     acc_to_smem<LP>(T1, acc, 1.0, lane);
   }
-  if (has_left) {
+  if (roleB && has_left) {
     acc_zero<LP>(acc);
     warp_gemm<LP, false, false, K_GE_N, false>(acc, T2, T0, lane);         // Q = G Di
     __syncwarp();
     acc_to_smem<LP>(T2, acc, 1.0, lane);
   }
-  __syncwarp();
+  team_sync();                                          // (2) P and Q are ready
   double wv = 0.0;
-  if (do_w) {
+  if (roleB && do_w) {
     wv = warp_matvec<LP, true>(T0, X, lane);                               // Di^T x_e
     if (has_odd) wv -= warp_matvec<LP, true>(T1, WT, lane);                // - P^T w~_e
     if (has_left) wv -= warp_matvec<LP, true>(T2, LWT, lane);              // - Q^T w~_{e-1}
     if (lane < LP) WV[lane] = wv;
-    __syncwarp();
   }
 
   const int lr = lane >> 2, lc = lane & 3;
@@ -169,66 +194,92 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     const bool vSd = is_aligned16(gSd), vSo = is_aligned16(gSo);
     double accE[NTL][NTL][2];
     acc_zero<LP>(accE);
-    if (valid) warp_gemm<LP, true, false, K_GE_MAX_MN, true>(accE, T0, T0, lane);     // Di^T Di (lower tiles)
-    __syncwarp();                                         // Di is dead: T0 may take N1
-    // N1 = S~_d[e] P + S~_o[e-1] Q ;  Sigma_{2e+1,2e} = -N1  -> So_out row 2e
-    if (has_odd) {
-      acc_zero<LP>(acc);
-      warp_gemm<LP, false, false, K_FULL, false>(acc, T3, T1, lane);
-      if (has_so) warp_gemm<LP, false, false, K_FULL, false>(acc, T4, T2, lane);
-      acc_to_smem<LP>(T0, acc, 1.0, lane);
-      T* dst = gSo + (size_t)(2 * e) * BS;
-#pragma unroll
-      for (int mt = 0; mt < NTL; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) {
-          const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
-          double v0 = -acc[mt][nt][0], v1 = -acc[mt][nt][1];
-          if (grad) {     // gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T)
-            const double wr = WT[row];
-            v0 = 2.0 * (gd * v0 - gm * wr * WV[col]);
-            v1 = 2.0 * (gd * v1 - gm * wr * WV[col + 1]);
-          }
-          frag_pair_store<T, L>(dst, row, col, v0, v1, vSo);
-        }
-    } else {
-      mma_fill_block<LP>(T0, false, lane);
-    }
-    // N2 = Q^T S~_d[e-1]^T + P^T S~_o[e-1] ;  Sigma_{2e,2e-1} = -N2  -> So_out row 2e-1 (or the halo block)
-    if (has_left) {
-      acc_zero<LP>(acc);
-      warp_gemm<LP, true, true, K_FULL, false>(acc, T2, LSD, lane);
-      if (has_so) warp_gemm<LP, true, false, K_FULL, false>(acc, T1, T4, lane);
-      __syncwarp();                                       // S~_o[e-1] has been read by every lane
-      acc_to_smem<LP>(T4, acc, 1.0, lane);
-      T* dst = e >= 1 ? (gSo != nullptr ? gSo + (size_t)(2 * e - 1) * BS : nullptr)
-                      : (a.So_halo_out != nullptr ? static_cast<T*>(a.So_halo_out) + (size_t)b * BS : nullptr);
-      if (dst != nullptr) {
-        const bool vec = e >= 1 ? vSo : is_aligned16(a.So_halo_out);
+    if (roleA && valid) warp_gemm<LP, true, false, K_GE_MAX_MN, true>(accE, T0, T0, lane);     // Di^T Di (lower tiles)
+    team_sync();                                          // (3) Di is dead (T0 may take N1), w_{2e} is published
+    // A: N1 = S~_d[e] P + S~_o[e-1] Q ;  Sigma_{2e+1,2e} = -N1  -> So_out row 2e
+    if (roleA) {
+      if (has_odd) {
+        acc_zero<LP>(acc);
+        warp_gemm<LP, false, false, K_FULL, false>(acc, T3, T1, lane);
+        if (has_so) warp_gemm<LP, false, false, K_FULL, false>(acc, T4, T2, lane);
+        acc_to_smem<LP>(T0, acc, 1.0, lane);
+        T* dst = gSo + (size_t)(2 * e) * BS;
 #pragma unroll
         for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) {
             const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
             double v0 = -acc[mt][nt][0], v1 = -acc[mt][nt][1];
-            if (grad) {   // gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)
-              const double wr = WV[row];
-              v0 = 2.0 * (gd * v0 - gm * wr * LWT[col]);
-              v1 = 2.0 * (gd * v1 - gm * wr * LWT[col + 1]);
+            if (grad) {     // gO_{2e} = 2 (gd Sigma_{2e+1,2e} - gm w~_e w_{2e}^T)
+              const double wr = WT[row];
+              v0 = 2.0 * (gd * v0 - gm * wr * WV[col]);
+              v1 = 2.0 * (gd * v1 - gm * wr * WV[col + 1]);
             }
-            frag_pair_store<T, L>(dst, row, col, v0, v1, vec);
+            frag_pair_store<T, L>(dst, row, col, v0, v1, vSo);
+          }
+      } else {
+        mma_fill_block<LP>(T0, false, lane);
+      }
+    }
+    // B: N2 = Q^T S~_d[e-1]^T + P^T S~_o[e-1] ;  Sigma_{2e,2e-1} = -N2  -> So_out row 2e-1 (or the halo block)
+    if (roleB && has_left) {
+      acc_zero<LP>(acc);
+      warp_gemm<LP, true, true, K_FULL, false>(acc, T2, LSD, lane);
+      if (has_so) warp_gemm<LP, true, false, K_FULL, false>(acc, T1, T4, lane);
+    }
+    team_sync();                                          // (4) S~_o[e-1] has been read by both products: T4 may take N2
+    if (roleB) {
+      if (has_left) {
+        acc_to_smem<LP>(T4, acc, 1.0, lane);
+        T* dst = e >= 1 ? (gSo != nullptr ? gSo + (size_t)(2 * e - 1) * BS : nullptr)
+                        : (a.So_halo_out != nullptr ? static_cast<T*>(a.So_halo_out) + (size_t)b * BS : nullptr);
+        if (dst != nullptr) {
+          const bool vec = e >= 1 ? vSo : is_aligned16(a.So_halo_out);
+#pragma unroll
+          for (int mt = 0; mt < NTL; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+              const int row = mt * 8 + lr, col = nt * 8 + 2 * lc;
+              double v0 = -acc[mt][nt][0], v1 = -acc[mt][nt][1];
+              if (grad) {   // gO_{2e-1} = 2 (gd Sigma_{2e,2e-1} - gm w_{2e} w~_{e-1}^T)
+                const double wr = WV[row];
+                v0 = 2.0 * (gd * v0 - gm * wr * LWT[col]);
+                v1 = 2.0 * (gd * v1 - gm * wr * LWT[col + 1]);
+              }
+              frag_pair_store<T, L>(dst, row, col, v0, v1, vec);
+            }
+        }
+      } else {
+        mma_fill_block<LP>(T4, false, lane);
+      }
+    }
+    __syncwarp();                                         // N1 (A) / N2 (B) written by this warp are visible to its own lanes
+    // Sigma_{2e,2e} = Di^T Di + P^T N1 (A) + Q^T N2^T (B; handed to A through the dead Q slot), lower tiles, mirrored through T1
+    if (valid) {
+      if (roleA && has_odd) warp_gemm<LP, true, false, K_FULL, true>(accE, T1, T0, lane);
+      if constexpr (TW == 1) {
+        if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
+      } else {
+        if (roleB) {
+          if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
+          __syncwarp();                                   // Q has been read by every lane of B (A is done with it since (4))
+          acc_to_smem<LP>(T2, accE, 1.0, lane);
+        }
+      }
+    }
+    team_sync();                                          // (5) B's part of Sigma_ee is in T2; P is dead for both warps
+    if (roleA && valid) {
+      if constexpr (TW == 2) {
+#pragma unroll
+        for (int mt = 0; mt < NTL; ++mt)
+#pragma unroll
+          for (int nt = 0; nt <= mt; ++nt) {
+            const double2 q = *reinterpret_cast<const double2*>(T2 + (mt * 8 + lr) * LD + nt * 8 + 2 * lc);
+            accE[mt][nt][0] += q.x;
+            accE[mt][nt][1] += q.y;
           }
       }
-    } else {
-      mma_fill_block<LP>(T4, false, lane);
-    }
-    __syncwarp();
-    // Sigma_{2e,2e} = Di^T Di + P^T N1 + Q^T N2^T  (lower tiles), mirrored through T1, -> Sd_out row 2e
-    if (valid) {
-      if (has_odd) warp_gemm<LP, true, false, K_FULL, true>(accE, T1, T0, lane);
-      if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
-      __syncwarp();                                       // P is dead: T1 is the mirror scratch
-      acc_to_smem<LP>(T1, accE, 1.0, lane);
+      acc_to_smem<LP>(T1, accE, 1.0, lane);               // T1 is the mirror scratch
       __syncwarp();
       acc_mirror_from_smem<LP>(accE, T1, 1.0, lane);
       T* dst = gSd + (size_t)(2 * e) * BS;
@@ -246,8 +297,8 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
           frag_pair_store<T, L>(dst, row, col, v0, v1, vSd);
         }
     }
-    // odd row copied through: Sigma_{2e+1,2e+1} = S~_d[e]   (gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T)
-    if (has_odd) {
+    // odd row copied through (B): Sigma_{2e+1,2e+1} = S~_d[e]   (gR_{2e+1} = gd S~_d[e] - gm w~_e w~_e^T)
+    if (roleB && has_odd) {
       T* dst = gSd + (size_t)(2 * e + 1) * BS;
       if (grad) {
         const double* wt = WT;
@@ -258,7 +309,7 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
       }
     }
   }
-  if (do_w && lane < L) {
+  if (roleB && do_w && lane < L) {
     T* gW = static_cast<T*>(a.w_out) + (size_t)b * a.stridew;
     const double sc = grad ? 2.0 * gm : 1.0;                // gx = 2 gm w
     if (valid) gW[(size_t)(2 * e) * L + lane] = (T)(sc * wv);
@@ -276,7 +327,7 @@ cudaError_t launch_mma_bwd(const LevelBwdArgs& a, cudaStream_t stream) {
   const long long grid = tiles * a.batch;
   if (grid <= 0) return cudaSuccess;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  cr_mma_bwd_kernel<T, L><<<(unsigned)grid, 32 * C::W, C::SMEM, stream>>>(a);
+  cr_mma_bwd_kernel<T, L><<<(unsigned)grid, 32 * C::W * C::TW, C::SMEM, stream>>>(a);
   return cudaGetLastError();
 }
 
