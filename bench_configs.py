@@ -265,7 +265,8 @@ def cfg5(reps, max_n, cpu_budget_ms=60e3):
             def loglik():
                 return cr.mahal_and_det(R, O, v)
 
-            row = {"l": l, "n": n, "gpu_posterior_ms": gpu_time(posterior, reps), "gpu_loglik_ms": gpu_time(loglik, reps)}
+            row = {"l": l, "n": n, "gpu_posterior_ms": gpu_time(posterior, reps), "gpu_loglik_ms": gpu_time(loglik, reps),
+                   "gpu_posterior_two_sweeps_ms": gpu_time(lambda: cr.solve_and_inverse_blocks(R, O, v), reps)}
             row["gpu_posterior_rows_per_s"] = n / (row["gpu_posterior_ms"] * 1e-3)
             est = None if last_ref is None else last_ref[1] * n / last_ref[0]
             if est is None or est <= cpu_budget_ms:

@@ -394,6 +394,23 @@ def inverse_blocks(decomp):
     return _to_caller(Sd, batched, caller), _to_caller(So, batched, caller)
 
 
+def solve_and_inverse_blocks(Rs, Os, y):
+    """``(J^{-1} y, Sig_diag, Sig_off)`` = ``solve(dec, y)`` and ``inverse_blocks(dec)`` of ``dec = decompose(Rs, Os)`` in TWO sweeps
+    instead of four: the forward sweep factorises and half-solves at once (as ``mahal_and_det`` does), one backward sweep carries
+    the back-substitution and the selected inverse together.  This is the in-sample posterior of the reference
+    (models.py:282-298: decompose, then solve, then inverse_blocks); not differentiable, like its caller."""
+    _check_blocks(Rs, Os)
+    dev = _engine.require_cuda()
+    batched, caller = Rs.dim() == 4, Rs.device
+    R = _batched(_dev(Rs.detach(), dev), batched)
+    O = _batched(_dev(Os.detach(), dev), batched)
+    Y = _batched(_dev(y.detach(), dev, R.dtype), batched)
+    pack = _forward_checked(R, O, Y, keep_factors=True)
+    Sd, So, w = _engine.backward_sweep(pack, sigma=True, w=True)
+    c = lambda t: _to_caller(t, batched, caller)
+    return c(w), c(Sd), c(So)
+
+
 def check_decompose_loop_outputs(num_dblocks, Ks_even, F, G, Rs, Os):
     """Shape check of one level's outputs (reference :262-280; there only the even branch can fire -- the odd one is guarded by
     ``!= 0 & num_dblocks > 1``, which parses as a chained comparison): E = ceil(m/2) factors, floor(m/2) F blocks and reduced

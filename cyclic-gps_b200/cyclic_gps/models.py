@@ -12,7 +12,7 @@ import torch
 from torch.optim import LBFGS, Adam
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
-from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_and_det, solve
+from cyclic_gps.cyclic_reduction import decompose, det, inverse_blocks, mahal_and_det, solve, solve_and_inverse_blocks
 from cyclic_gps.model_utils import build_2x2_block, build_3x3_block, compute_eG, gaussian_stitch
 from cyclic_gps.peg import peg_precision
 
@@ -171,14 +171,10 @@ class LEGFamily(_Base):
         (reference models.py:282-298); computed on the GPU, returned on the caller's device."""
         dev = self._compute_device(ts)
         _, shift = self._obs_terms()
-        K = {}
-        K["Rs"], K["Os"] = self._precision_blocks(ts, shift)
-        dec = decompose(**K)
-        mean = solve(dec, self.compute_v(xs.to(dev)))
-        cov = {}
-        cov["Rs"], cov["Os"] = inverse_blocks(dec)
+        Rs, Os = self._precision_blocks(ts, shift)
+        mean, Sd, So = solve_and_inverse_blocks(Rs, Os, self.compute_v(xs.to(dev)))     # two sweeps: factor + half-solve, back-solve + selected inverse
         out = ts.device
-        return mean.to(out), {k: v.to(out) for k, v in cov.items()}
+        return mean.to(out), {"Rs": Sd.to(out), "Os": So.to(out)}
 
     def log_likelihood(self, ts, xs):
         """log p(xs | ts) (reference models.py:301-372: two CR factorisations; here the prior's log-determinant comes out of the

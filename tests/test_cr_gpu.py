@@ -472,6 +472,34 @@ def test_inverse_blocks_is_differentiable(l, n, dtype, batched):
     assert_close(Sd2, Sd.detach(), 0.0 if dtype == torch.float64 else tol, "same forward")
 
 
+@pytest.mark.parametrize("l,n,dtype,batched", [(1, 1, torch.float64, False), (3, 33, torch.float64, True), (8, 1000, torch.float32, True),
+                                                (16, 257, torch.float64, False), (5, 2, torch.float64, False)])
+def test_solve_and_inverse_blocks_is_the_reference_sequence(l, n, dtype, batched):
+    """The in-sample posterior in two sweeps (forward with the right-hand side, backward with back-solve + selected inverse)
+    against decompose -> solve -> inverse_blocks (reference models.py:282-298) and against the oracle."""
+    c = cr()
+    tol = TOL[dtype]
+    series = [leg_inputs(l, n, dtype, seed=3 * l + n + b) for b in range(3 if batched else 1)]
+    st = (lambda xs: torch.stack(xs)) if batched else (lambda xs: xs[0])
+    R, O, x = (st([s[i] for s in series]).cuda() for i in range(3))
+    w, Sd, So = c.solve_and_inverse_blocks(R, O, x)
+    dec = c.decompose(R, O)
+    w2 = c.solve(dec, x)
+    Sd2, So2 = c.inverse_blocks(dec)
+    assert_close(w, w2, tol, "mean vs solve")
+    assert_close(Sd, Sd2, tol, "Sigma_d vs inverse_blocks")
+    if n > 1:
+        assert_close(So, So2, tol, "Sigma_o vs inverse_blocks")
+    for b, (Rb, Ob, xb) in enumerate(series):
+        dec_o = orc.factor(Rb.double(), Ob.double())
+        sd, so = orc.selected_inverse(dec_o)
+        pick = (lambda t: t[b]) if batched else (lambda t: t)
+        assert_close(pick(w), orc.solve(dec_o, xb.double()), tol, "mean vs oracle")
+        assert_close(pick(Sd), sd, tol, "Sigma_d vs oracle")
+        if n > 1:
+            assert_close(pick(So), so, tol, "Sigma_o vs oracle")
+
+
 def test_check_decompose_loop_outputs_like_the_reference():
     """reference cyclic_reduction.py:262-280: the shape check of one level (AssertionError on a mismatch)."""
     c = cr()
