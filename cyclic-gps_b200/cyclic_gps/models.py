@@ -266,10 +266,26 @@ class LEGFamily(_Base):
         return zm @ B.T, B.unsqueeze(0) @ zv @ B.T.unsqueeze(0)
 
     # ---- training hooks (reference models.py:374-392)
+    # Opt-in: evaluate the training loss through cyclic_gps.graphs.GraphedLogLikelihood (one CUDA-graph replay for the device part of
+    # the likelihood and its backward).  The reference's training loop feeds the SAME (ts, xs) every step (models.py:374-392); the
+    # runner is rebuilt whenever the batch differs from the one it was captured for.
+    graphed_training = False
+
+    def _graphed_loss(self, t, x):
+        from cyclic_gps.graphs import GraphedLogLikelihood
+        cache = getattr(self, "_graph_cache", None)
+        if cache is None or cache[0].shape != t.shape or cache[1].shape != x.shape or not (torch.equal(cache[0], t) and torch.equal(cache[1], x)):
+            cache = (t.clone(), x.clone(), GraphedLogLikelihood(self, t, x))
+            object.__setattr__(self, "_graph_cache", cache)
+        return cache[2]()
+
     def training_step(self, train_batch, batch_idx):
         t, x = train_batch
         nobs = x.shape[0] * x.shape[1] * x.shape[2]
-        loss = -self.log_likelihood(t.squeeze(0), x.squeeze(0)) / nobs
+        if self.graphed_training and torch.cuda.is_available():
+            loss = -self._graphed_loss(t.squeeze(0), x.squeeze(0)) / nobs
+        else:
+            loss = -self.log_likelihood(t.squeeze(0), x.squeeze(0)) / nobs
         self.log("NLL", loss)
         return loss
 

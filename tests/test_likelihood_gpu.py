@@ -199,3 +199,29 @@ def test_graphed_log_likelihood_matches_eager(rank, d, B, n, dtype, tol_v, tol_g
             for nm in names:
                 p = getattr(model, nm)
                 p.add_(0.03 * torch.randn(p.shape, dtype=p.dtype, device=p.device, generator=None))
+
+
+def test_graphed_training_step_is_the_eager_one():
+    """LEGFamily.graphed_training = True: training_step through the CUDA-graph runner gives the eager loss and gradients, step after
+    step with an optimiser moving the parameters, and notices a different batch."""
+    from cyclic_gps.models import LEGFamily
+    torch.manual_seed(11)
+    n = 300
+    ts = torch.cumsum(torch.rand(n, dtype=torch.float64) + 0.1, 0)
+    xs = torch.randn(n, 2, dtype=torch.float64)
+    a = LEGFamily(rank=6, obs_dim=2, train=True, data_type=torch.float64)
+    b = LEGFamily(rank=6, obs_dim=2, train=True, data_type=torch.float64)
+    b.load_state_dict(a.state_dict())
+    b.graphed_training = True
+    oa, ob = torch.optim.Adam(a.parameters(), lr=1e-2), torch.optim.Adam(b.parameters(), lr=1e-2)
+    for it in range(4):
+        if it == 3:
+            xs = xs + 0.1                                   # a new batch: the runner must be rebuilt, not replayed
+        batch = (ts.unsqueeze(0), xs.unsqueeze(0))
+        oa.zero_grad(); ob.zero_grad()
+        la, lb = a.training_step(batch, it), b.training_step(batch, it)
+        la.backward(); lb.backward()
+        assert_close(lb, la, 1e-10, f"loss, step {it}")
+        for (na, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert_close(pb.grad, pa.grad, 1e-8, f"grad {na}, step {it}")
+        oa.step(); ob.step()
