@@ -47,6 +47,7 @@ template <typename T, int L>
 __global__ void __launch_bounds__(32 * MmaBwdCfg<T, L>::W * MmaBwdCfg<T, L>::TW, MmaBwdCfg<T, L>::MIN_CTAS)
 cr_mma_bwd_kernel(const LevelBwdArgs a) {
   using C = MmaBwdCfg<T, L>;
+  constexpr int KP = MmaGeom<L>::KP, LA = MmaGeom<L>::LA;
   constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NT = C::NT, NTL = LP / 8, BS = L * L, TW = C::TW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -162,19 +163,19 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     const double mine = 1.0 / T0[r * LD + r];
 #pragma unroll
     for (int j = 0; j < LP; ++j) invd[j] = __shfl_sync(0xffffffffu, mine, j);
-    warp_tri_inverse<LP>(T0, invd, lane);               // T0 = Di
+    warp_tri_inverse<LP, LA>(T0, invd, lane);               // T0 = Di
   }
   team_sync();                                          // (1) Di is ready
   double acc[NTL][NTL][2];
   if (roleA && has_odd) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_GE_N, false>(acc, T1, T0, lane);         // P = F Di
+    warp_gemm<LP, false, false, K_GE_N, false, KP>(acc, T1, T0, lane);         // P = F Di
     __syncwarp();
     acc_to_smem<LP>(T1, acc, 1.0, lane);
   }
   if (roleB && has_left) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_GE_N, false>(acc, T2, T0, lane);         // Q = G Di
+    warp_gemm<LP, false, false, K_GE_N, false, KP>(acc, T2, T0, lane);         // Q = G Di
     __syncwarp();
     acc_to_smem<LP>(T2, acc, 1.0, lane);
   }
@@ -194,14 +195,14 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     const bool vSd = is_aligned16(gSd), vSo = is_aligned16(gSo);
     double accE[NTL][NTL][2];
     acc_zero<LP>(accE);
-    if (roleA && valid) warp_gemm<LP, true, false, K_GE_MAX_MN, true>(accE, T0, T0, lane);     // Di^T Di (lower tiles)
+    if (roleA && valid) warp_gemm<LP, true, false, K_GE_MAX_MN, true, KP>(accE, T0, T0, lane);     // Di^T Di (lower tiles)
     team_sync();                                          // (3) Di is dead (T0 may take N1), w_{2e} is published
     // A: N1 = S~_d[e] P + S~_o[e-1] Q ;  Sigma_{2e+1,2e} = -N1  -> So_out row 2e
     if (roleA) {
       if (has_odd) {
         acc_zero<LP>(acc);
-        warp_gemm<LP, false, false, K_FULL, false>(acc, T3, T1, lane);
-        if (has_so) warp_gemm<LP, false, false, K_FULL, false>(acc, T4, T2, lane);
+        warp_gemm<LP, false, false, K_FULL, false, KP>(acc, T3, T1, lane);
+        if (has_so) warp_gemm<LP, false, false, K_FULL, false, KP>(acc, T4, T2, lane);
         acc_to_smem<LP>(T0, acc, 1.0, lane);
         T* dst = gSo + (size_t)(2 * e) * BS;
 #pragma unroll
@@ -224,8 +225,8 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     // B: N2 = Q^T S~_d[e-1]^T + P^T S~_o[e-1] ;  Sigma_{2e,2e-1} = -N2  -> So_out row 2e-1 (or the halo block)
     if (roleB && has_left) {
       acc_zero<LP>(acc);
-      warp_gemm<LP, true, true, K_FULL, false>(acc, T2, LSD, lane);
-      if (has_so) warp_gemm<LP, true, false, K_FULL, false>(acc, T1, T4, lane);
+      warp_gemm<LP, true, true, K_FULL, false, KP>(acc, T2, LSD, lane);
+      if (has_so) warp_gemm<LP, true, false, K_FULL, false, KP>(acc, T1, T4, lane);
     }
     team_sync();                                          // (4) S~_o[e-1] has been read by both products: T4 may take N2
     if (roleB) {
@@ -256,12 +257,12 @@ cr_mma_bwd_kernel(const LevelBwdArgs a) {
     __syncwarp();                                         // N1 (A) / N2 (B) written by this warp are visible to its own lanes
     // Sigma_{2e,2e} = Di^T Di + P^T N1 (A) + Q^T N2^T (B; handed to A through the dead Q slot), lower tiles, mirrored through T1
     if (valid) {
-      if (roleA && has_odd) warp_gemm<LP, true, false, K_FULL, true>(accE, T1, T0, lane);
+      if (roleA && has_odd) warp_gemm<LP, true, false, K_FULL, true, KP>(accE, T1, T0, lane);
       if constexpr (TW == 1) {
-        if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
+        if (has_left) warp_gemm<LP, true, true, K_FULL, true, KP>(accE, T2, T4, lane);
       } else {
         if (roleB) {
-          if (has_left) warp_gemm<LP, true, true, K_FULL, true>(accE, T2, T4, lane);
+          if (has_left) warp_gemm<LP, true, true, K_FULL, true, KP>(accE, T2, T4, lane);
           __syncwarp();                                   // Q has been read by every lane of B (A is done with it since (4))
           acc_to_smem<LP>(T2, accE, 1.0, lane);
         }

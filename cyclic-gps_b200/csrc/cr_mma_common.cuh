@@ -24,6 +24,8 @@ struct MmaGeom {
   static constexpr int LD = LP + 4;              // leading dimension (doubles)
   static constexpr int BLK = LP * LD;            // doubles per block
   static constexpr int NTL = LP / 8;             // 8 x 8 tiles per side
+  static constexpr int KP = (L + 3) / 4 * 4;     // inner dimension of the products: the padding beyond it is zero (or a unit diagonal against zeros)
+  static constexpr int LA = (L + 1) / 2 * 2;     // active size of the serial parts (Cholesky, triangular inverse): the padding is the identity
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -47,14 +49,16 @@ __device__ __forceinline__ constexpr bool k_active(int kt, int mt, int nt) {
 // acc (+)= op(A) op(B) over the whole LP x LP block by ONE warp.
 //   op(A)[m][k] = TA ? A[k][m] : A[m][k]        op(B)[k][n] = TB ? B[n][k] : B[k][n]
 // acc[mt][nt][0..1] is the C fragment of tile (mt, nt).  LOWER: only tiles with mt >= nt are computed.
-template <int LP, bool TA, bool TB, int KR, bool LOWER>
+// KP: inner dimension actually summed (a multiple of 4, >= ell): blocks are zero beyond ell -- or carry a unit diagonal that only ever
+// meets zeros there -- so the k-steps over the padding contribute nothing and are skipped.
+template <int LP, bool TA, bool TB, int KR, bool LOWER, int KP = LP>
 __device__ __forceinline__ void warp_gemm(double (&acc)[LP / 8][LP / 8][2], const double* __restrict__ A, const double* __restrict__ B, const int lane) {
   constexpr int LD = LP + 4, NTL = LP / 8;
   const int lr = lane >> 2, lc = lane & 3;
   const double* pa = TA ? A + lc * LD + lr : A + lr * LD + lc;
   const double* pb = TB ? B + lr * LD + lc : B + lc * LD + lr;
 #pragma unroll
-  for (int k0 = 0; k0 < LP; k0 += 4) {
+  for (int k0 = 0; k0 < KP; k0 += 4) {
     const int kt = k0 >> 3;
     double af[NTL], bf[NTL];
 #pragma unroll
@@ -340,7 +344,8 @@ __device__ __forceinline__ void mma_store_block(T* __restrict__ g, const double*
 // (`colbuf`, 2 * LP doubles) and every lane applies the rank-1 update to the rest of its row -- LP - j independent
 // FMAs, so the serial chain per column is only pivot broadcast -> rsqrt -> scale -> publish.
 // invd[j] = 1 / K[j][j] on every lane.  Returns true when a pivot was not positive.
-template <int LP>
+// LA (even, >= ell): the block is the identity beyond it, so columns j >= LA need no work (invd = 1) and row updates stop at LA.
+template <int LP, int LA = LP>
 __device__ __forceinline__ bool warp_cholesky(double* S, double* colbuf, double (&invd)[LP], const int lane) {
   constexpr int LD = LP + 4;
   const bool act = lane < LP;
@@ -353,7 +358,9 @@ __device__ __forceinline__ bool warp_cholesky(double* S, double* colbuf, double 
   }
   bool bad = false;
 #pragma unroll
-  for (int j = 0; j < LP; ++j) {
+  for (int j = LA; j < LP; ++j) invd[j] = 1.0;
+#pragma unroll
+  for (int j = 0; j < LA; ++j) {
     const double d = __shfl_sync(0xffffffffu, a[j], j);
     if (!(d > 0.0)) bad = true;
     const double inv = rsqrt(d);
@@ -364,9 +371,9 @@ __device__ __forceinline__ bool warp_cholesky(double* S, double* colbuf, double 
     if (act) cb[r] = l;
     __syncwarp();
     // a[c] -= L[r][j] L[c][j] for c > j (entries with c > r are never used)
-    if (((j + 1) & 1) != 0 && j + 1 < LP) a[j + 1] = fma(-l, cb[j + 1], a[j + 1]);
+    if (((j + 1) & 1) != 0 && j + 1 < LA) a[j + 1] = fma(-l, cb[j + 1], a[j + 1]);
 #pragma unroll
-    for (int c = (j + 2) & ~1; c < LP; c += 2) {
+    for (int c = (j + 2) & ~1; c < LA; c += 2) {
       const double2 t = *reinterpret_cast<const double2*>(cb + c);
       a[c] = fma(-l, t.x, a[c]);
       a[c + 1] = fma(-l, t.y, a[c + 1]);
@@ -384,7 +391,7 @@ __device__ __forceinline__ bool warp_cholesky(double* S, double* colbuf, double 
 // S <- S^{-1} for lower-triangular S with 1 / diag in invd.  Lane r builds ROW r of the inverse by a column sweep from
 // the right (y^T K = e_r^T): y_c = acc_c / K_cc, then acc_c' -= y_c K[c][c'] for c' < c -- the updates of one step are
 // independent of each other and read row c of K as a broadcast, so the serial chain per step is one multiply + one FMA.
-template <int LP>
+template <int LP, int LA = LP>
 __device__ __forceinline__ void warp_tri_inverse(double* S, const double (&invd)[LP], const int lane) {
   constexpr int LD = LP + 4;
   const bool act = lane < LP;
@@ -393,7 +400,7 @@ __device__ __forceinline__ void warp_tri_inverse(double* S, const double (&invd)
 #pragma unroll
   for (int c = 0; c < LP; ++c) acc[c] = (c == r) ? 1.0 : 0.0;
 #pragma unroll
-  for (int c = LP - 1; c >= 0; --c) {
+  for (int c = LA - 1; c >= 0; --c) {       // (columns >= LA: identity rows and columns, nothing to eliminate)
     const double y = acc[c] * invd[c];      // Ki[r][c] (exactly zero for c > r)
     acc[c] = y;
 #pragma unroll

@@ -46,6 +46,7 @@ template <typename T, int L>
 __global__ void __launch_bounds__(32 * MmaFwdCfg<T, L>::W, MmaFwdCfg<T, L>::MIN_CTAS)
 cr_mma_fwd_kernel(const LevelFwdArgs a) {
   using C = MmaFwdCfg<T, L>;
+  constexpr int KP = MmaGeom<L>::KP, LA = MmaGeom<L>::LA;
   constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, OWN = C::OWN, NTL = LP / 8, BS = L * L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +110,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   double ld_part = 0.0, mh_part = 0.0;
   {
     double invd[LP];
-    const bool bad = warp_cholesky<LP>(S0, CB, invd, lane);
+    const bool bad = warp_cholesky<LP, LA>(S0, CB, invd, lane);
     if (own) {
       if (bad && a.info != nullptr && lane == 0) {
         const long long flat = (long long)b * E + e;
@@ -123,7 +124,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
       }
       if (a.D != nullptr) mma_store_block<T, L, LP>(static_cast<T*>(a.D) + ((size_t)b * E + e) * BS, S0, lane, is_aligned16(a.D));
     }
-    warp_tri_inverse<LP>(S0, invd, lane);     // S0 = Ki
+    warp_tri_inverse<LP, LA>(S0, invd, lane);     // S0 = Ki
   }
   if (has_y) {
     const double xr = warp_matvec<LP, false>(S0, YE, lane);     // x = Ki y_even
@@ -140,7 +141,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   double acc[NTL][NTL][2];
   if (do_f) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_LE_N, false>(acc, S2, S0, lane);          // F = O_right Ki^T
+    warp_gemm<LP, false, true, K_LE_N, false, KP>(acc, S2, S0, lane);          // F = O_right Ki^T
     __syncwarp();
     acc_to_smem<LP>(S2, acc, 1.0, lane);
     __syncwarp();
@@ -148,7 +149,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   }
   if (has_left) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, true, true, K_LE_N, false>(acc, S3, S0, lane);           // G = O_left^T Ki^T
+    warp_gemm<LP, true, true, K_LE_N, false, KP>(acc, S3, S0, lane);           // G = O_left^T Ki^T
     __syncwarp();
     acc_to_smem<LP>(S3, acc, 1.0, lane);
     __syncwarp();
@@ -173,14 +174,14 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
     T* base = static_cast<T*>(e >= 1 ? a.On : a.On_halo);
     if (base != nullptr) {
       acc_zero<LP>(acc);
-      warp_gemm<LP, false, true, K_FULL, false>(acc, S2, S3, lane);        // F G^T
+      warp_gemm<LP, false, true, K_FULL, false, KP>(acc, S2, S3, lane);        // F G^T
       T* dst = base + ((e >= 1) ? ((size_t)b * (o - 1) + (e - 1)) * BS : (size_t)b * BS);
       acc_to_global<T, L, LP>(dst, acc, -1.0, lane, is_aligned16(base));   // O~_{e-1} = -F G^T
     }
   }
   if (need_B) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, S3, S3, lane);          // B = G G^T
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, S3, S3, lane);          // B = G G^T
     if (warp == 0) {
       // link to the virtual node -1 (chunk-partitioned series): accumulate -G G^T and -G x there
       if (a.Rh_acc != nullptr) {
@@ -207,7 +208,7 @@ cr_mma_fwd_kernel(const LevelFwdArgs a) {
   if (warp > 0) pair_arrive(warp);                    // B and G x of this node are in shared memory (barrier id = consumer warp + 1)
   if (do_f) {
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, S2, S2, lane);          // A = F F^T, kept in registers
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, S2, S2, lane);          // A = F F^T, kept in registers
   }
   if (do_f) {                                         // R_odd has landed in S0
     cp_async_wait_all();

@@ -72,6 +72,7 @@ __device__ __forceinline__ void pegw_expansion(double* S, const double* cre, con
 template <typename T, int L>
 __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_F, 1) cr_pegw_fwd_kernel(const PegFwdArgs a) {
   using C = PegwCfg<T, L>;
+  constexpr int KP = MmaGeom<L>::KP, LA = MmaGeom<L>::LA;
   constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NTL = LP / 8, W = C::W_F, OWN = W - 1, BS = L * L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_F, 1) cr_pegw_fwd_kernel
     pegw_expansion<L, LP>(SA, cre, cim, a.M_re, a.M_im, nterms, 0.0, lane);          // D
     // K = -(D + D^T + D D^T), identity on the padded diagonal
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, SA, SA, lane);
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, SA, SA, lane);
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
@@ -116,22 +117,22 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_F, 1) cr_pegw_fwd_kernel
       }
     __syncwarp();
     double invd[LP];
-    bad = warp_cholesky<LP>(SK, CB, invd, lane);
+    bad = warp_cholesky<LP, LA>(SK, CB, invd, lane);
     if (a.logdet != nullptr && warp >= 1 && lane == 0) {
       double p = 1.0;
 #pragma unroll
       for (int j = 0; j < L; ++j) p *= invd[j];
       ld = 2.0 * log(p);                                   // -logdet(I - A A^T) = -2 sum log K_jj
     }
-    warp_tri_inverse<LP>(SK, invd, lane);                  // SK = Ki
+    warp_tri_inverse<LP, LA>(SK, invd, lane);                  // SK = Ki
     if (lane < L) SA[lane * LD + lane] += 1.0;             // SA = A
     __syncwarp();
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_FULL, false>(acc, SK, SA, lane);        // Ki A
+    warp_gemm<LP, false, false, K_FULL, false, KP>(acc, SK, SA, lane);        // Ki A
     acc_to_smem<LP>(SB, acc, 1.0, lane);
     __syncwarp();
     acc_zero<LP>(acc);
-    warp_gemm<LP, true, false, K_FULL, false>(acc, SK, SB, lane);         // B = Ki^T (Ki A)
+    warp_gemm<LP, true, false, K_FULL, false, KP>(acc, SK, SB, lane);         // B = Ki^T (Ki A)
     __syncwarp();
     acc_to_smem<LP>(SB, acc, 1.0, lane);
     if (warp >= 1) {                                       // O_g = -B (the halo warp's gap belongs to the previous CTA)
@@ -140,9 +141,9 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_F, 1) cr_pegw_fwd_kernel
     }
     __syncwarp();
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, SB, SA, lane);         // P - I = B A^T
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, SB, SA, lane);         // P - I = B A^T
     acc_to_smem<LP>(SK, acc, 1.0, lane);                                  // (Ki is dead)
-    warp_gemm<LP, true, false, K_FULL, false>(accQ, SA, SB, lane);        // Q - I = A^T B
+    warp_gemm<LP, true, false, K_FULL, false, KP>(accQ, SA, SB, lane);        // Q - I = A^T B
   } else {
     mma_fill_block<LP>(SK, false, lane);
   }
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_F, 1) cr_pegw_fwd_kernel
 template <typename T, int L>
 __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel(const PegBwdArgs a) {
   using C = PegwCfg<T, L>;
+  constexpr int KP = MmaGeom<L>::KP, LA = MmaGeom<L>::LA;
   constexpr int LP = C::LP, LD = C::LD, BLK = C::BLK, NTL = LP / 8, W = C::W_B, BS = L * L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel
     __syncwarp();
     // T1 = Us - H A^T  -> ST
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, SH, SA, lane);
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, SH, SA, lane);
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel
     acc_to_smem<LP>(SW, sym, 1.0, lane);                                   // SW = Ws
     // X1 = T1 B - H  -> SX
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_FULL, false>(acc, ST, SB, lane);
+    warp_gemm<LP, false, false, K_FULL, false, KP>(acc, ST, SB, lane);
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel
     __syncwarp();                                                          // T1 consumed, Ws and X1 visible
     // T2 = Ws A^T - H^T  -> ST
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, true, K_FULL, false>(acc, SW, SA, lane);
+    warp_gemm<LP, false, true, K_FULL, false, KP>(acc, SW, SA, lane);
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
@@ -278,8 +280,8 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel
     __syncwarp();                                                          // T2 visible, H consumed
     // Y3 = Ws + T2 B + A^T X1  -> SH
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_FULL, false>(acc, ST, SB, lane);
-    warp_gemm<LP, true, false, K_FULL, false>(acc, SA, SX, lane);
+    warp_gemm<LP, false, false, K_FULL, false, KP>(acc, ST, SB, lane);
+    warp_gemm<LP, true, false, K_FULL, false, KP>(acc, SA, SX, lane);
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
 #pragma unroll
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(32 * PegwCfg<T, L>::W_B, 1) cr_pegw_bwd_kernel
     __syncwarp();
     // gA = X1 + B Y3 + 2 gld B
     acc_zero<LP>(acc);
-    warp_gemm<LP, false, false, K_FULL, false>(acc, SB, SH, lane);
+    warp_gemm<LP, false, false, K_FULL, false, KP>(acc, SB, SH, lane);
     double* out = a.gA + (size_t)vg * BS;
 #pragma unroll
     for (int mt = 0; mt < NTL; ++mt)
