@@ -6,6 +6,7 @@
 #include "crb200.h"
 #include "cr_multi.h"
 #include <cstdlib>
+#include <cstdint>
 
 namespace crb200 {
 #define CRB_DECL(TN, LO, HI)                                                                         \
@@ -45,6 +46,14 @@ inline char* adv(void* p, long long elems, int es) { return p ? static_cast<char
 inline const char* adv(const void* p, long long elems, int es) { return p ? static_cast<const char*>(p) + elems * es : nullptr; }
 
 bool bad_common(int dtype, int ell) { return (dtype != CRB200_F32 && dtype != CRB200_F64) || ell < 1 || ell > 32; }
+
+// packed lower triangles: only the thread-per-node family implements them (automatic choice for every size that offers them)
+int tri_stride(int dtype, int ell) { return crb200::tri_stride_elems(dtype == CRB200_F32 ? 4 : 8, ell); }
+bool bad_tri(int dtype, int ell, int tri, int variant, bool halo) {
+  if (tri == 0) return false;
+  return tri_stride(dtype, ell) == 0 || halo || (tri & ~3) != 0 || (variant != CRB200_AUTO && variant != CRB200_THREAD_PER_NODE);
+}
+bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 
 // fused deep-level kernels (thread-per-node family); ma == nullptr only asks whether they exist for (dtype, ell)
 cudaError_t fwd_multi(int dtype, int ell, const crb200::MultiArgs<crb200_fwd_args>* ma, cudaStream_t s) {
@@ -121,6 +130,8 @@ int crb200_level_fwd(int dtype, int ell, const crb200_fwd_args* a, void* stream)
   if (a->m > 3 && a->On == nullptr) return CRB200_EINVAL;
   if (a->y != nullptr && a->m > 1 && a->yn == nullptr) return CRB200_EINVAL;
   if (a->O_halo != nullptr && (a->Rh_acc == nullptr || a->On_halo == nullptr || (keep && a->G_halo == nullptr))) return CRB200_EINVAL;
+  if (bad_tri(dtype, ell, a->tri, a->variant, a->O_halo != nullptr)) return CRB200_EINVAL;
+  if (((a->tri & 1) != 0 && misaligned16(a->R)) || ((a->tri & 2) != 0 && (misaligned16(a->D) || misaligned16(a->Rn)))) return CRB200_EINVAL;
   if (a->batch == 0) return CRB200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CRB200_F32) { CRB_RANGES(CRB_FWD, f32) } else { CRB_RANGES(CRB_FWD, f64) }
@@ -141,6 +152,8 @@ int crb200_level_bwd(int dtype, int ell, const crb200_bwd_args* a, void* stream)
     if (sig && (a->Sd_halo == nullptr || a->So_halo_out == nullptr || (a->m > 1 && a->So_halo_in == nullptr))) return CRB200_EINVAL;
     if (w && a->w_halo == nullptr) return CRB200_EINVAL;
   }
+  if (bad_tri(dtype, ell, a->tri, a->variant, a->G_halo != nullptr) || ((a->tri & 2) != 0 && a->grad_mode != 0)) return CRB200_EINVAL;
+  if (((a->tri & 1) != 0 && (misaligned16(a->D) || misaligned16(a->Sd_in))) || ((a->tri & 2) != 0 && misaligned16(a->Sd_out))) return CRB200_EINVAL;
   if (a->batch == 0) return CRB200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CRB200_F32) { CRB_RANGES(CRB_BWD, f32) } else { CRB_RANGES(CRB_BWD, f64) }
@@ -165,8 +178,10 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
   if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->R == nullptr) return CRB200_EINVAL;
   if (a->nlevels > max_levels(a->n)) return CRB200_EINVAL;   // checked before anything is launched
+  if (a->tri != 0 && (bad_tri(dtype, ell, 3, a->variant, a->O_halo != nullptr) || a->nlevels != max_levels(a->n))) return CRB200_EINVAL;
   const int es = dtype == CRB200_F32 ? 4 : 8;
   const long long bs = (long long)ell * ell, B = a->batch;
+  const long long dbs = a->tri != 0 ? tri_stride(dtype, ell) : bs;      // elements per diagonal block of the reduced systems
   crb200_fwd_args l{};
   l.batch = a->batch;
   l.R = a->R; l.O = a->O; l.y = a->y;
@@ -201,6 +216,7 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
     const long long E = (m + 1) / 2, o = m / 2, g = (m - 1) / 2;
     const int slot = k & 1;
     l.m = m;
+    l.tri = a->tri != 0 ? ((k > 0 ? 1 : 0) | 2) : 0;         // level 0 reads the caller's full blocks
     l.D = adv(a->D, B * bs * offE, es);
     l.F = o > 0 ? adv(a->F, B * bs * offO, es) : nullptr;
     l.G = g > 0 ? adv(a->G, B * bs * offG, es) : nullptr;
@@ -234,7 +250,7 @@ int crb200_sweep_fwd(int dtype, int ell, const crb200_sweep_fwd_args* a, void* s
     }
     if (halo != nullptr) halo = a->On_halo[slot];
     l.R = l.Rn; l.O = l.On; l.y = l.yn;
-    l.strideR = o * bs; l.strideO = (o > 1 ? o - 1 : 0) * bs; l.stridey = o * ell;
+    l.strideR = o * dbs; l.strideO = (o > 1 ? o - 1 : 0) * bs; l.stridey = o * ell;
     offE += E; offO += o; offG += g;
     m = (int)o;
   }
@@ -281,8 +297,11 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
   if (bad_common(dtype, ell)) return CRB200_EUNSUPPORTED;
   if (a->batch < 0 || a->n < 1 || a->nlevels < 1 || a->nlevels > 40 || a->D == nullptr) return CRB200_EINVAL;
   if (a->nlevels > max_levels(a->n)) return CRB200_EINVAL;
+  if (a->tri != 0 && (bad_tri(dtype, ell, 3, a->variant, a->G_halo != nullptr) || a->nlevels != max_levels(a->n) || a->top_Sd != nullptr))
+    return CRB200_EINVAL;
   const int es = dtype == CRB200_F32 ? 4 : 8;
   const long long bs = (long long)ell * ell, B = a->batch;
+  const long long dbs = a->tri != 0 ? tri_stride(dtype, ell) : bs;
   int ms[40];
   long long offE[40], offO[40], offG[40];
   {
@@ -317,6 +336,7 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
     const long long o = m / 2, g = (m - 1) / 2;
     const int slot = k & 1;
     l.m = m;
+    l.tri = a->tri != 0 ? (1 | (k > 0 ? 2 : 0)) : 0;         // level 0 writes the caller's full blocks
     l.D = adv(a->D, B * bs * offE[k], es);
     l.F = o > 0 ? adv(a->F, B * bs * offO[k], es) : nullptr;
     l.G = g > 0 ? adv(a->G, B * bs * offG[k], es) : nullptr;
@@ -332,7 +352,7 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
       l.Sd_out = sig ? adv(a->scrSd[slot], off * bs, es) : nullptr;
       l.So_out = (sig && m > 1) ? adv(a->scrSo[slot], off * bs, es) : nullptr;
       l.w_out = w ? adv(a->scrw[slot], off * ell, es) : nullptr;
-      l.strideSd = (long long)m * bs; l.strideSo = (long long)(m > 1 ? m - 1 : 0) * bs; l.stridew = (long long)m * ell;
+      l.strideSd = (long long)m * dbs; l.strideSo = (long long)(m > 1 ? m - 1 : 0) * bs; l.stridew = (long long)m * ell;
       l.gm = nullptr; l.gd = nullptr; l.grad_mode = 0;
     }
     if (a->G_halo != nullptr) {
@@ -358,6 +378,8 @@ int crb200_sweep_bwd(int dtype, int ell, const crb200_sweep_bwd_args* a, void* s
   }
   return CRB200_OK;
 }
+
+int crb200_tri_stride(int dtype, int ell) { return bad_common(dtype, ell) ? 0 : tri_stride(dtype, ell); }
 
 int crb200_fwd_tile_nodes(int dtype, int ell) {
   if (bad_common(dtype, ell)) return 0;

@@ -9,6 +9,10 @@ namespace crb200 {
 constexpr int kMultiMax = 12;      // levels per fused launch (12 x ~220 B of arguments < the 4 KB parameter space)
 constexpr int kMultiWarps = 4;
 
+// Packed lower triangles (crb200_*_args.tri, crb200_tri_stride): elements per packed block where the thread-per-node kernels
+// offer that storage, else 0.  float32, ell = 8: 36 of 64 elements, a multiple of 16 bytes like the full block.
+constexpr int tri_stride_elems(int elem_size, int ell) { return (elem_size == 4 && ell == 8) ? 36 : 0; }
+
 template <typename Args>
 struct MultiArgs {
   int count;

@@ -72,10 +72,17 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   const int nF = cmax(0, cmin(NT, o - e0));                      // odd neighbours e0 .. of this tile
   const int ilo = (e0 == 0) ? 1 : 0;
   const int nodd = cmin(e0 + NT, o) - (e0 - 1 + ilo);            // deeper node e0-1+i -> record i
+  // packed lower triangles (crb200_bwd_args.tri, cr_tpn_common.cuh): D and S~_d arrive packed / Sigma_d leaves packed (inner levels)
+  using TP = TriPack<T, L>;
+  constexpr bool TRI = TP::OK && Cf::COMPACT;
+  constexpr int PKS = TRI ? TP::PKS : BS;
+  const bool tri_in = TRI && (a.tri & 1) != 0;
+  const bool tri_out = TRI && (a.tri & 2) != 0;
 
   // ---------------- stage in, first group: factors D, F, G and the vectors ----------------
   {
-    rec_g2s<T, BS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * BS, 0, nE, is_aligned16(a.D));
+    if (tri_in) rec_g2s<T, PKS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * PKS, 0, nE, is_aligned16(a.D));
+    else rec_g2s<T, BS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * BS, 0, nE, is_aligned16(a.D));
     rec_g2s<T, BS, 1>(rec1 + Cf::B * ES, nsb, static_cast<const T*>(a.F) + ((size_t)b * o + e0) * BS, 0, nF, is_aligned16(a.F));
     const int gf = (e0 == 0) ? 1 : 0;
     rec_g2s<T, BS, 1>(rec1 + Cf::C * ES, nsb, static_cast<const T*>(a.G) + ((size_t)b * gcnt + (e0 + gf - 1)) * BS, gf, nE - gf,
@@ -94,8 +101,12 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   // S~_d of the deeper level (record i <- deeper node e0-1+i); COMPACT: second use of the A slots
   auto stage_Sd = [&]() {
     if (do_sigma) {
-      rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * BS, ilo, nodd,
-                        is_aligned16(a.Sd_in));
+      if (tri_in)
+        rec_g2s<T, PKS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * PKS, ilo, nodd,
+                           is_aligned16(a.Sd_in));
+      else
+        rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * BS, ilo, nodd,
+                          is_aligned16(a.Sd_in));
       if (e0 == 0 && halo)
         rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_halo) + (size_t)b * BS, 0, 1, is_aligned16(a.Sd_halo));
     }
@@ -122,9 +133,9 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   const bool sd_vec = is_aligned16(gSd);
   auto out_Sd = [&]() {
     if (do_sigma) {
-      if constexpr (Cf::COMPACT)   // Sigma_{2e+1,2e+1} only (record i+1 -> Sd_out row 2(e0+i)+1); the even rows left from registers
-        rec_s2g_strided<T, BS, 2>(gSd + (size_t)(row_lo + 1) * BS, rec1 + Cf::SD * ES, nsb, 0, nF, sd_vec);
-      else                         // A and SD are adjacent: rows 2e, 2e+1 leave as pairs
+      if constexpr (Cf::COMPACT) { // Sigma_{2e+1,2e+1} only (record i+1 -> Sd_out row 2(e0+i)+1); the even rows left from registers
+        if (!tri_out) rec_s2g_strided<T, BS, 2>(gSd + (size_t)(row_lo + 1) * BS, rec1 + Cf::SD * ES, nsb, 0, nF, sd_vec);   // (packed: left at the expansion)
+      } else                         // A and SD are adjacent: rows 2e, 2e+1 leave as pairs
         rec_s2g<T, BS, 2>(gSd + (size_t)row_lo * BS, rec1 + Cf::A * ES, nsb, 0, nrows, sd_vec);
     }
   };
@@ -194,7 +205,10 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
 
   // neutral operands for boundary lanes (rare, hence divergent code is fine): no node -> D = I; no odd
   // neighbour -> F = 0, w~_e = 0; no left link -> G = 0 (and the never-loaded left record is cleared)
-  if (!valid) smem_fill_identity<T, L>(N + Cf::A);
+  if (!valid) {
+    if constexpr (TRI) { if (tri_in) smem_fill_identity_tri<T, L>(N + Cf::A); else smem_fill_identity<T, L>(N + Cf::A); }
+    else smem_fill_identity<T, L>(N + Cf::A);
+  }
   if (!has_odd) { smem_fill_zero<T, BS>(N + Cf::B); smem_fill_zero<T, L>(N + Cf::WT); }
   if (!has_left) smem_fill_zero<T, BS>(N + Cf::C);
   if (!valid) smem_fill_zero<T, L>(N + Cf::X);
@@ -205,12 +219,25 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   T Mx[L][L];   // Di = D^{-1} (lower triangular), later the lower triangle of Sigma_{2e,2e}; only r >= c is used
   T dxs[L];
   {
+    bool k_loaded = false;
+    if constexpr (TRI) {
+      if (tri_in) {
 #pragma unroll
-    for (int r = 0; r < L; ++r) {
-      T row[L];
-      lds_row<T, L>(row, N + Cf::A + r * L);
+        for (int r = 0; r < L; ++r)
 #pragma unroll
-      for (int c = 0; c < L; ++c) Mx[r][c] = row[c];   // holds K for now
+          for (int c = 0; c < L; ++c) Mx[r][c] = T(0);
+        lds_tri<T, L>(Mx, N + Cf::A);
+        k_loaded = true;
+      }
+    }
+    if (!k_loaded) {
+#pragma unroll
+      for (int r = 0; r < L; ++r) {
+        T row[L];
+        lds_row<T, L>(row, N + Cf::A + r * L);
+#pragma unroll
+        for (int c = 0; c < L; ++c) Mx[r][c] = row[c];   // holds K for now
+      }
     }
     if constexpr (Cf::COMPACT) {
       __syncwarp();                // every lane has its D in registers: the A slots are free
@@ -317,6 +344,14 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
 
   cp_async_wait_group<0>();        // S~_d, S~_o have landed
   __syncwarp();
+  if constexpr (TRI) {
+    if (tri_in && do_sigma) {      // packed S~_d -> full symmetric rows, in place (the products below read rows of this and of the left record)
+      // inner levels: Sigma_{2e+1,2e+1} = S~_d[e] leaves right here, still packed, from the registers of the expansion
+      tri_expand_inplace<T, L>(N + Cf::SD, (tri_out && valid && e < o) ? gSd + (size_t)(2 * e + 1) * PKS : nullptr);
+      tri_expand_inplace_warp<T, L>(S + Cf::SD, lane);
+      __syncwarp();
+    }
+  }
   if (do_sigma) {
     if (!has_so) smem_fill_zero<T, BS>(N + Cf::SO);
     if (lane == 0 && e0 == 0 && !halo) smem_fill_zero<T, BS>(S + Cf::SD);
@@ -422,8 +457,11 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
 #pragma unroll
           for (int c = 0; c < L; ++c) row[c] = gd * row[c] - gm * wv[r] * wv[c];
         }
-        if constexpr (Cf::COMPACT) stg_row<T, L>(dst + r * L, row, sd_vec);
+        if constexpr (Cf::COMPACT) { if (!tri_out) stg_row<T, L>(dst + r * L, row, sd_vec); }
         else sts_row<T, L>(N + Cf::A + r * L, row);
+      }
+      if constexpr (TRI) {
+        if (tri_out) st_tri<T, L>(gSd + (size_t)(2 * e) * PKS, Mx);     // (inner level: no gradient scaling)
       }
     }
   }

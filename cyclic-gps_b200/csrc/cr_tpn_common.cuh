@@ -67,6 +67,27 @@ __device__ __forceinline__ int4 lds128_u32(unsigned saddr) {
   return v;
 }
 
+// Chunk walk for units of CPU 16-byte chunks when neither 32 % CPU nor CPU % 32 is zero (packed lower triangles: CPU = 9), one unit per
+// record: fully unrolled over the at most MAXU units of a tile, so that a chunk costs one compare + select for the record wrap and
+// immediates for everything else (the generic path divides per chunk).  f(saddr, j, wrap): lane's chunk number lane + 32 j.
+constexpr int kMaxTileUnits = 33;
+template <int CPU, int MAXU, typename F>
+__device__ __forceinline__ void chunk_walk(unsigned srec0, unsigned nsb, int kstart, int nunits, F f) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned k0 = lane + (unsigned)kstart * CPU;
+  const unsigned q0 = k0 / CPU, c0 = k0 - q0 * CPU;
+  const unsigned base = srec0 + q0 * nsb + c0 * 16;
+  const int total = nunits * CPU;
+  constexpr int J = (MAXU * CPU + 31) / 32;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const unsigned a = (32u * j) / CPU, b = (32u * j) % CPU;
+    const bool wrap = (b != 0) && (c0 >= CPU - b);
+    const unsigned saddr = base + a * nsb + b * 16 + (wrap ? nsb - CPU * 16 : 0u);
+    if ((int)lane + 32 * j < total) f(saddr, j, wrap);
+  }
+}
+
 // Global units (UE elements each, contiguous) -> records.  Units are grouped GRP per record
 // (GRP = 1: one unit per record; GRP = 2: units 2t, 2t+1 are adjacent fields of record t).
 // Unit index k = kstart + j goes to record k / GRP, sub-field k % GRP.
@@ -102,6 +123,10 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
         }
         return;
       }
+      if constexpr (GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
+        chunk_walk<CPR, kMaxTileUnits>(srec0, nsb, kstart, nunits, [&](unsigned saddr, int j, bool) { cp_async16_u32(saddr, gp + 512 * j); });
+        return;
+      }
       for (int i = lane; i < total; i += 32, gp += 512) {
         const unsigned k = (unsigned)(i + kstart * CPU);
         const unsigned rec = k / CPR, c = k - rec * CPR;
@@ -135,6 +160,17 @@ __device__ __forceinline__ void rec_g2s_strided(unsigned srec0, unsigned nsb, co
         const unsigned sstep = (32 / CPU) * nsb;
         constexpr size_t gstep = (size_t)(32 / CPU) * GS * CPU * 16;
         for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) cp_async16_u32(saddr, gp);
+        return;
+      }
+      if constexpr (CPU < 32) if (nunits <= kMaxTileUnits) {
+        // unit u = q0 + a + wrap, chunk c = c0 + b - CPU * wrap: the global side skips (GS - 1) units at every wrap
+        const unsigned q0 = (unsigned)lane / CPU, c0 = (unsigned)lane - q0 * CPU;
+        const char* g0 = reinterpret_cast<const char*>(g) + ((size_t)q0 * GS * CPU + c0) * 16;
+        const char* g1 = g0 + (size_t)(GS - 1) * CPU * 16;
+        chunk_walk<CPU, kMaxTileUnits>(srec0 + kstart * nsb, nsb, 0, nunits, [&](unsigned saddr, int j, bool wrap) {
+          const unsigned a = (32u * j) / CPU, b = (32u * j) % CPU;
+          cp_async16_u32(saddr, (wrap ? g1 : g0) + ((size_t)a * GS * CPU + b) * 16);
+        });
         return;
       }
       for (int i = lane; i < total; i += 32) {
@@ -212,6 +248,10 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
         }
         return;
       }
+      if constexpr (GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
+        chunk_walk<CPR, kMaxTileUnits>(srec0, nsb, kstart, nunits, [&](unsigned saddr, int j, bool) { *reinterpret_cast<int4*>(gp + 512 * j) = lds128_u32(saddr); });
+        return;
+      }
       for (int i = lane; i < total; i += 32, gp += 512) {
         const unsigned k = (unsigned)(i + kstart * CPU);
         const unsigned rec = k / CPR, c = k - rec * CPR;
@@ -247,6 +287,16 @@ __device__ __forceinline__ void rec_s2g_strided(T* __restrict__ g, unsigned srec
         for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) *reinterpret_cast<int4*>(gp) = lds128_u32(saddr);
         return;
       }
+      if constexpr (CPU < 32) if (nunits <= kMaxTileUnits) {
+        const unsigned q0 = (unsigned)lane / CPU, c0 = (unsigned)lane - q0 * CPU;
+        char* g0 = reinterpret_cast<char*>(g) + ((size_t)q0 * GS * CPU + c0) * 16;
+        char* g1 = g0 + (size_t)(GS - 1) * CPU * 16;
+        chunk_walk<CPU, kMaxTileUnits>(srec0 + kstart * nsb, nsb, 0, nunits, [&](unsigned saddr, int j, bool wrap) {
+          const unsigned a = (32u * j) / CPU, b = (32u * j) % CPU;
+          *reinterpret_cast<int4*>((wrap ? g1 : g0) + ((size_t)a * GS * CPU + b) * 16) = lds128_u32(saddr);
+        });
+        return;
+      }
       for (int i = lane; i < total; i += 32) {
         const unsigned j = (unsigned)i / CPU, c = (unsigned)i - j * CPU;
         *reinterpret_cast<int4*>(reinterpret_cast<char*>(g) + ((size_t)j * GS * CPU + c) * 16) = lds128_u32(srec0 + (kstart + j) * nsb + c * 16);
@@ -280,6 +330,107 @@ __device__ __forceinline__ void smem_fill_identity(T* p) {
   for (int r = 0; r < L; ++r)
 #pragma unroll
     for (int c = 0; c < L; ++c) p[r * L + c] = (r == c) ? T(1) : T(0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Packed lower triangles (crb200_*_args.tri): the symmetric / triangular blocks that never leave the library in the
+// fused likelihood path -- D (Cholesky factors), R~ (reduced diagonal blocks) and Sigma_d of the inner levels -- travel
+// through HBM as the ell (ell + 1) / 2 entries of their lower triangle, row after row, padded to a multiple of 16 bytes
+// (PKS elements per block).  Shared-memory slots keep their full size: the packed payload lands at the start of the
+// slot and is expanded / compacted there by the thread that owns the node.  Offered where the thread-per-node kernels
+// use the three-blocks-per-node layout and both block sizes are multiples of 16 bytes: ell = 8 in float32, the
+// configuration the headline metric is quoted on (36 instead of 64 elements: -14 % bytes over a whole step).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int L>
+struct TriPack {
+  static constexpr int VE = 16 / (int)sizeof(T);
+  static constexpr int PK = L * (L + 1) / 2;
+  static constexpr int PKS = (PK + VE - 1) / VE * VE;
+  static constexpr bool OK = tri_stride_elems((int)sizeof(T), L) != 0;
+  static_assert(!OK || (tri_stride_elems((int)sizeof(T), L) == PKS && (L * L) % VE == 0 && L % VE == 0), "packed blocks and full blocks must be 16-byte multiples");
+};
+__host__ __device__ constexpr int tri_index(int r, int c) { return r * (r + 1) / 2 + c; }
+
+// packed block in shared memory -> flat registers
+template <typename T, int L>
+__device__ __forceinline__ void lds_tri_flat(T (&f)[TriPack<T, L>::PKS], const T* p) {
+  lds_row<T, TriPack<T, L>::PKS>(f, p);
+}
+// packed block in shared memory -> lower triangle of M (entries above the diagonal are left alone)
+template <typename T, int L>
+__device__ __forceinline__ void lds_tri(T (&M)[L][L], const T* p) {
+  T f[TriPack<T, L>::PKS];
+  lds_tri_flat<T, L>(f, p);
+#pragma unroll
+  for (int r = 0; r < L; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) M[r][c] = f[tri_index(r, c)];
+}
+// lower triangle of M -> packed block (shared or global memory, 16-byte aligned)
+template <typename T, int L>
+__device__ __forceinline__ void st_tri(T* p, const T (&M)[L][L]) {
+  T f[TriPack<T, L>::PKS];
+#pragma unroll
+  for (int i = TriPack<T, L>::PK; i < TriPack<T, L>::PKS; ++i) f[i] = T(0);
+#pragma unroll
+  for (int r = 0; r < L; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) f[tri_index(r, c)] = M[r][c];
+  sts_row<T, TriPack<T, L>::PKS>(p, f);
+}
+// in place, one block owned by the calling thread: packed payload at the start of the slot -> full symmetric L x L rows
+template <typename T, int L>
+__device__ __forceinline__ void tri_expand_inplace(T* p, T* copy_to = nullptr) {
+  T f[TriPack<T, L>::PKS];
+  lds_tri_flat<T, L>(f, p);
+  if (copy_to != nullptr) sts_row<T, TriPack<T, L>::PKS>(copy_to, f);      // the packed block passes through (16-byte stores, any state space)
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+    T row[L];
+#pragma unroll
+    for (int c = 0; c < L; ++c) row[c] = (c <= r) ? f[tri_index(r, c)] : f[tri_index(c, r)];
+    sts_row<T, L>(p + r * L, row);
+  }
+}
+// The same for ONE block by the whole warp (a record no lane owns): lane j < 4 L gathers 16 bytes of the full block, the warp
+// syncs, the lanes store.
+template <typename T, int L>
+__device__ __forceinline__ void tri_expand_inplace_warp(T* p, const int lane) {
+  constexpr int VE = TriPack<T, L>::VE;
+  static_assert(L * L / VE <= 32, "one 16-byte chunk of the full block per lane");
+  T v[VE];
+  const int r = (lane * VE) / L, c0 = (lane * VE) % L;
+  if (lane < L * L / VE) {
+#pragma unroll
+    for (int i = 0; i < VE; ++i) {
+      const int c = c0 + i;
+      v[i] = p[c <= r ? tri_index(r, c) : tri_index(c, r)];
+    }
+  }
+  __syncwarp();
+  if (lane < L * L / VE) sts_row<T, VE>(p + lane * VE, v);
+}
+// ... and back: lower triangle of the full rows -> packed payload at the start of the slot
+template <typename T, int L>
+__device__ __forceinline__ void tri_compact_inplace(T* p) {
+  T f[TriPack<T, L>::PKS];
+#pragma unroll
+  for (int i = TriPack<T, L>::PK; i < TriPack<T, L>::PKS; ++i) f[i] = T(0);
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+    T row[L];
+    lds_row<T, L>(row, p + r * L);
+#pragma unroll
+    for (int c = 0; c <= r; ++c) f[tri_index(r, c)] = row[c];
+  }
+  sts_row<T, TriPack<T, L>::PKS>(p, f);
+}
+template <typename T, int L>
+__device__ __forceinline__ void smem_fill_identity_tri(T* p) {
+#pragma unroll
+  for (int r = 0; r < L; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) p[tri_index(r, c)] = (r == c) ? T(1) : T(0);
 }
 
 // compiler-only fence: stops the scheduler from hoisting later shared-memory loads above this

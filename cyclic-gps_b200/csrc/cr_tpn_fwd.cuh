@@ -57,6 +57,11 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   const bool has_y = a.y != nullptr;
   const bool halo = a.O_halo != nullptr;
   const int lane = threadIdx.x & 31;
+  // packed lower triangles (crb200_fwd_args.tri, cr_tpn_common.cuh): R comes in packed (levels >= 1 of a fused sweep) / D and R~ leave packed
+  using TP = TriPack<T, L>;
+  constexpr int PKS = TP::OK ? TP::PKS : BS;
+  const bool tri_in = TP::OK && (a.tri & 1) != 0;
+  const bool tri_out = TP::OK && (a.tri & 2) != 0;
 
   const T* gR = static_cast<const T*>(a.R) + (size_t)b * a.strideR;
   const T* gO = static_cast<const T*>(a.O) + (size_t)b * a.strideO;
@@ -69,7 +74,8 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
-    rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, (nR + 1) >> 1, is_aligned16(gR));   // even rows
+    if (tri_in) rec_g2s_strided<T, PKS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * PKS, 0, (nR + 1) >> 1, is_aligned16(gR));
+    else rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, (nR + 1) >> 1, is_aligned16(gR));   // even rows
     if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
     cp_async_commit();
     const int pfirst = (r0 == 0) ? 1 : 0;
@@ -84,8 +90,10 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   const int n_own = cmin(OWN, E - e0);
   const int n_odd = cmax(0, cmin(OWN, o - e0));
   auto out_D_x = [&]() {
-    if (a.D != nullptr)
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+    if (a.D != nullptr) {
+      if (tri_out) rec_s2g<T, PKS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+      else rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+    }
     if (a.xk != nullptr && has_y)
       rec_s2g<T, L, 1>(static_cast<T*>(a.xk) + ((size_t)b * E + e0) * L, s0 + C::YE * ES, nsb, 0, n_own, is_aligned16(a.xk));
   };
@@ -104,7 +112,8 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   };
   auto out_reduced = [&]() {
     if (a.Rn != nullptr && n_odd > 0) {
-      rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+      if (tri_out) rec_s2g<T, PKS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+      else rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
       if (has_y && a.yn != nullptr)
         rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
     }
@@ -113,7 +122,8 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   auto stage_R_odd = [&]() {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
-    rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * BS, 0, nR >> 1, is_aligned16(gR));
+    if (tri_in) rec_g2s_strided<T, PKS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * PKS, 0, nR >> 1, is_aligned16(gR));
+    else rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * BS, 0, nR >> 1, is_aligned16(gR));
     cp_async_commit();
   };
 
@@ -149,16 +159,33 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
 
   // neutral operands for lanes without a node (R = I, y = 0), written once into the lane's own record so that
   // the dense algebra below needs no per-element selects
-  if (!valid) { smem_fill_identity<T, L>(N + C::RE); smem_fill_zero<T, L>(N + C::YE); }
+  if (!valid) {
+    if constexpr (TP::OK) { if (tri_in) smem_fill_identity_tri<T, L>(N + C::RE); else smem_fill_identity<T, L>(N + C::RE); }
+    else smem_fill_identity<T, L>(N + C::RE);
+    smem_fill_zero<T, L>(N + C::YE);
+  }
   T K[L][L];
   T inv[L];
   bool bad = false;
+  bool k_loaded = false;
+  if constexpr (TP::OK) {
+    if (tri_in) {                // only the lower triangle is ever read
 #pragma unroll
-  for (int r = 0; r < L; ++r) {
-    T row[L];
-    lds_row<T, L>(row, N + C::RE + r * L);
+      for (int r = 0; r < L; ++r)
 #pragma unroll
-    for (int c = 0; c < L; ++c) K[r][c] = row[c];
+        for (int c = 0; c < L; ++c) K[r][c] = T(0);
+      lds_tri<T, L>(K, N + C::RE);
+      k_loaded = true;
+    }
+  }
+  if (!k_loaded) {
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      T row[L];
+      lds_row<T, L>(row, N + C::RE + r * L);
+#pragma unroll
+      for (int c = 0; c < L; ++c) K[r][c] = row[c];
+    }
   }
   double dprod = 1.0;
 #pragma unroll
@@ -177,12 +204,18 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
       for (int r = c; r < L; ++r) K[r][c] = fma(-K[r][k], K[c][k], K[r][c]);
   }
   if (valid) {
+    bool k_stored = false;
+    if constexpr (TP::OK) {
+      if (tri_out) { st_tri<T, L>(N + C::RE, K); k_stored = true; }
+    }
+    if (!k_stored) {
 #pragma unroll
-    for (int r = 0; r < L; ++r) {
-      T row[L];
+      for (int r = 0; r < L; ++r) {
+        T row[L];
 #pragma unroll
-      for (int c = 0; c < L; ++c) row[c] = (c <= r) ? K[r][c] : T(0);
-      sts_row<T, L>(N + C::RE + r * L, row);
+        for (int c = 0; c < L; ++c) row[c] = (c <= r) ? K[r][c] : T(0);
+        sts_row<T, L>(N + C::RE + r * L, row);
+      }
     }
   }
   if (bad && own && a.info != nullptr) {
@@ -349,17 +382,42 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   __syncwarp();
   if (do_f) {
     // (no even node e+1: the lane to the right holds G = 0, so B and v arrive as zeros)
+    bool r_done = false;
+    if constexpr (TP::OK) {
+      if (tri_out) {               // lower triangle only: R~ leaves packed (the next level's Cholesky reads nothing else)
+        T Rm[L][L];
+        if (tri_in) {
+          lds_tri<T, L>(Rm, N + C::RE);
+        } else {
 #pragma unroll
-    for (int r = 0; r < L; ++r) {
-      T row[L];
-      lds_row<T, L>(row, N + C::RE + r * L);
+          for (int r = 0; r < L; ++r) {
+            T row[L];
+            lds_row<T, L>(row, N + C::RE + r * L);
 #pragma unroll
-      for (int c = 0; c < L; ++c) {
-        const T av = (r >= c) ? A[r][c] : A[c][r];
-        const T bv = (r >= c) ? Bn[r][c] : Bn[c][r];
-        row[c] = row[c] - av - bv;
+            for (int c = 0; c <= r; ++c) Rm[r][c] = row[c];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < L; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) Rm[r][c] = Rm[r][c] - A[r][c] - Bn[r][c];
+        st_tri<T, L>(N + C::RE, Rm);
+        r_done = true;
       }
-      sts_row<T, L>(N + C::RE + r * L, row);
+    }
+    if (!r_done) {
+#pragma unroll
+      for (int r = 0; r < L; ++r) {
+        T row[L];
+        lds_row<T, L>(row, N + C::RE + r * L);
+#pragma unroll
+        for (int c = 0; c < L; ++c) {
+          const T av = (r >= c) ? A[r][c] : A[c][r];
+          const T bv = (r >= c) ? Bn[r][c] : Bn[c][r];
+          row[c] = row[c] - av - bv;
+        }
+        sts_row<T, L>(N + C::RE + r * L, row);
+      }
     }
     if (has_y) {
       T yo[L];

@@ -28,7 +28,7 @@ class FwdArgs(C.Structure):
                 ("D", _vp), ("F", _vp), ("G", _vp), ("xk", _vp),
                 ("Rn", _vp), ("On", _vp), ("yn", _vp),
                 ("logdet", _vp), ("mahal", _vp), ("acc_slots", _i), ("info", _vp),
-                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp), ("variant", _i)]
+                ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp), ("Rh_acc", _vp), ("yh_acc", _vp), ("variant", _i), ("tri", _i)]
 
 
 class BwdArgs(C.Structure):
@@ -38,7 +38,7 @@ class BwdArgs(C.Structure):
                 ("Sd_out", _vp), ("So_out", _vp), ("w_out", _vp),
                 ("strideSd", _ll), ("strideSo", _ll), ("stridew", _ll),
                 ("gm", _vp), ("gd", _vp), ("grad_mode", _i),
-                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp), ("So_halo_out", _vp), ("variant", _i)]
+                ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp), ("So_halo_out", _vp), ("variant", _i), ("tri", _i)]
 
 
 class HsArgs(C.Structure):
@@ -56,7 +56,7 @@ class SweepFwdArgs(C.Structure):
                 ("scrR", _vp * 2), ("scrO", _vp * 2), ("scry", _vp * 2),
                 ("logdet", _vp), ("mahal", _vp), ("info", _vp), ("acc_slots", _i),
                 ("O_halo", _vp), ("G_halo", _vp), ("On_halo", _vp * 2), ("Rh_acc", _vp), ("yh_acc", _vp),
-                ("variant", _i)]
+                ("variant", _i), ("tri", _i)]
 
 
 class SweepBwdArgs(C.Structure):
@@ -69,7 +69,7 @@ class SweepBwdArgs(C.Structure):
                 ("gm", _vp), ("gd", _vp), ("grad_mode", _i),
                 ("G_halo", _vp), ("Sd_halo", _vp), ("w_halo", _vp), ("So_halo_in", _vp),
                 ("So_halo", _vp * 2), ("So_halo_out", _vp),
-                ("variant", _i)]
+                ("variant", _i), ("tri", _i)]
 
 
 class SweepHsArgs(C.Structure):
@@ -97,7 +97,7 @@ class PegBwdArgs(C.Structure):
 
 EXPORTS = ("crb200_peg_precision_fwd", "crb200_peg_precision_bwd", "crb200_peg_max_ell", "crb200_peg_sum_max_ell", "crb200_version", "crb200_max_ell", "crb200_last_cuda_error", "crb200_level_fwd",
            "crb200_level_bwd", "crb200_level_halfsolve", "crb200_sweep_fwd", "crb200_sweep_bwd", "crb200_sweep_halfsolve",
-           "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_launch_count")
+           "crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_launch_count", "crb200_tri_stride")
 
 _lib = None
 _lock = threading.Lock()
@@ -145,7 +145,7 @@ def load():
         lib.crb200_peg_max_ell.argtypes = []
         lib.crb200_peg_sum_max_ell.restype = _i
         lib.crb200_peg_sum_max_ell.argtypes = []
-        for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes"):
+        for name in ("crb200_fwd_tile_nodes", "crb200_bwd_tile_nodes", "crb200_tri_stride"):
             getattr(lib, name).restype = _i
             getattr(lib, name).argtypes = [_i, _i]
         _lib = lib
@@ -276,6 +276,17 @@ def launch_count() -> int:
 def tracing() -> bool:
     tr = TRACE
     return tr is not None and getattr(tr, "enabled", True)
+
+
+# Packed lower triangles for the blocks that stay inside the library (crb200.h `tri`): CRB200_TRI=0 switches them off.
+TRI = os.environ.get("CRB200_TRI", "1") != "0"
+
+
+def tri_stride(dtype: torch.dtype, ell: int) -> int:
+    """Elements per packed lower triangle where the level kernels offer that storage (float32, ell = 8), else 0."""
+    if not TRI or VARIANT not in (0, 2):
+        return 0
+    return int(load().crb200_tri_stride(dtype_code(dtype), ell))
 
 
 def tile_nodes(dtype: torch.dtype, ell: int):

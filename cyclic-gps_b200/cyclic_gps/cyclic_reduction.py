@@ -479,11 +479,11 @@ class _MahalAndDetFn(torch.autograd.Function):
         X = _batched(_dev(x, dev, Rs.dtype), batched)
         need = any(ctx.needs_input_grad[:3])
         if need and not EAGER_PD_CHECK:
-            pack = _engine.forward_sweep(R, O, X, keep_factors=need)
+            pack = _engine.forward_sweep(R, O, X, keep_factors=need, internal=True)
             ctx.deferred = _engine.DeferredCheck([pack])         # (no jitter retry in the deferred mode)
         else:
             ctx.deferred = None
-            pack = _forward_checked(R, O, X, keep_factors=need)
+            pack = _forward_checked(R, O, X, keep_factors=need, internal=True)
         ctx.pack = pack if need else None
         ctx.batched, ctx.devs = batched, (Rs.device, Os.device, x.device)
         mh, ld = pack.mahal.to(Rs.dtype), pack.logdet.to(Rs.dtype)

@@ -38,7 +38,7 @@ class GraphedMahalAndDet:
             self._out = self._run()
 
     def _run(self):
-        pack = _engine.forward_sweep(self.R, self.O, self.x, keep_factors=True)
+        pack = _engine.forward_sweep(self.R, self.O, self.x, keep_factors=True, internal=True)
         gR, gO, gx = _engine.backward_sweep(pack, sigma=True, w=True, grad=(self.gm, self.gd))
         return pack.mahal.to(self.R.dtype), pack.logdet.to(self.R.dtype), gR, gO, gx, pack
 
@@ -131,7 +131,7 @@ class GraphedLogLikelihood:
         v = self.xs * self.p_W.reshape(l) if one else self.xs @ self.p_W
         white = self.xs * self.p_Linv.reshape(1) if one else self.xs @ self.p_Linv
         obs_mahal = (white * self.xs).sum(dim=(-1, -2), dtype=torch.float64)
-        pack = _engine.forward_sweep(R, O, v, keep_factors=True)
+        pack = _engine.forward_sweep(R, O, v, keep_factors=True, internal=True)
         gR, gO, gv = _engine.backward_sweep(pack, sigma=True, w=True, grad=(self.gm, self.gd))
         gG, gshift = peg.builder_backward(c, self.gaps, O, gR, gO, self.gpl, dtype)
         gW = torch.einsum("bnd,bnl->dl", self.xs.double(), gv.double())

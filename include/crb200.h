@@ -71,6 +71,9 @@ typedef struct crb200_fwd_args {
   /* left halo (chunk-partitioned series): virtual surviving node -1 coupled to row 0 by O_halo */
   const void* O_halo; void* G_halo; void* On_halo; void* Rh_acc; void* yh_acc;   /* (batch,l,l)x4, (batch,l) */
   int variant;                                        /* CRB200_AUTO, or force one kernel family (tests, benchmarks) */
+  int tri;                                            /* packed lower triangles (crb200_tri_stride(dtype, ell) elements per block, 0 = not
+                                                         offered): bit 0 = R is packed (strideR counts packed elements), bit 1 = D and Rn
+                                                         are written packed.  0 = full blocks everywhere */
 } crb200_fwd_args;
 
 /* One CR level, backward direction (deepest level first).  Replaces the per-level bodies of
@@ -89,6 +92,8 @@ typedef struct crb200_bwd_args {
   int grad_mode;                                                 /* 0: Sigma / w ; 1: gR / gO / gx     */
   const void* G_halo; const void* Sd_halo; const void* w_halo; const void* So_halo_in; void* So_halo_out;
   int variant;
+  int tri;                                                       /* bit 0 = D and Sd_in are packed lower triangles, bit 1 = Sd_out is written
+                                                                    packed (strideSd counts packed elements; never with grad_mode) */
 } crb200_bwd_args;
 
 /* Half solve against stored factors.  Replaces one iteration of halfsolve (:318-333):
@@ -125,6 +130,9 @@ typedef struct crb200_sweep_fwd_args {
   const void* O_halo; void* G_halo;                   /* G_halo: nlevels * batch blocks (NULL => not kept) */
   void* On_halo[2]; void* Rh_acc; void* yh_acc;
   int variant;
+  int tri;                                            /* 1: D and the reduced diagonal blocks of the scratch are packed lower triangles (block stride
+                                                         crb200_tri_stride; every level keeps the offset it has with full blocks).  Only for a full
+                                                         reduction without halo whose factors go to crb200_sweep_bwd with tri = 1 and nowhere else */
 } crb200_sweep_fwd_args;
 
 /* Backward = backhalfsolve (:341-377) + inverse_blocks (:470-503) + gradient assembly, deepest level first.
@@ -141,6 +149,7 @@ typedef struct crb200_sweep_bwd_args {
   const void* G_halo; const void* Sd_halo; const void* w_halo; const void* So_halo_in;
   void* So_halo[2]; void* So_halo_out;
   int variant;
+  int tri;                                            /* 1: D was written by crb200_sweep_fwd with tri = 1; the inner levels then also pass Sigma_d packed */
 } crb200_sweep_bwd_args;
 
 /* All levels of halfsolve (:312-338) / mahal (:461-467) against packed factors: X receives x_k of every level
@@ -214,6 +223,10 @@ long long crb200_launch_count(void);
 int crb200_level_fwd(int dtype, int ell, const crb200_fwd_args* args, void* stream);
 int crb200_level_bwd(int dtype, int ell, const crb200_bwd_args* args, void* stream);
 int crb200_level_halfsolve(int dtype, int ell, const crb200_hs_args* args, void* stream);
+
+/* Elements per packed lower triangle (ell (ell + 1) / 2 rounded up to 16 bytes) where the level kernels offer the `tri`
+ * storage of the symmetric / triangular blocks (float32, ell = 8: 36 instead of 64), else 0. */
+int crb200_tri_stride(int dtype, int ell);
 
 /* Tile geometry, for the roofline bookkeeping in bench.py: even nodes owned per CTA. */
 int crb200_fwd_tile_nodes(int dtype, int ell);
