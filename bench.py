@@ -794,6 +794,10 @@ def main():
                 "whole_step": {"algo_bytes": bytes_per_row_total(ell, s) * B * n,
                                "achieved": bytes_per_row_total(ell, s) * B * n / (ms / args.steps * 1e-3) / 1e9,
                                "frac": bytes_per_row_total(ell, s) * B * n / (ms / args.steps * 1e-3) / 1e9 / peak}}
+    from cyclic_gps import _native as _nat
+    pks = _nat.tri_stride(dtype, ell)
+    roofline["storage"] = (f"packed lower triangles inside the library ({pks} of {ell * ell} elements for D, the reduced diagonal blocks and Sigma_d of "
+                           "the inner levels): real traffic is below the algorithmic bytes that `achieved` counts (SURVEY 8(d))") if pks else "full blocks"
     # DRAM bytes of that kernel from the committed ncu --set full capture, scaled to this launch's rows
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
