@@ -617,6 +617,41 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
     return e2e, train
 
 
+def time_graphed(rk, tensors, steps, warmup):
+    """The same loglik+grad step through cyclic_gps.graphs.GraphedMahalAndDet: ONE CUDA-graph replay per step instead of Python,
+    autograd and allocator work around ~12-18 launches (what bounds the strong-scaling step at 128 series per GPU).  Returns ms
+    for `steps` steps, max over ranks, or None if the graph could not be built."""
+    from cyclic_gps.graphs import GraphedMahalAndDet
+    dist = rk.dist
+    try:
+        gr = GraphedMahalAndDet(*[t.detach() for t in tensors], g_mahal=-0.5, g_det=-0.5)
+    except Exception:  # noqa: BLE001
+        return None
+
+    def step():
+        mh, ld, gR, gO, gx = gr(gr.R, gr.O, gr.x)              # static buffers: nothing is copied, the gradients land in gR / gO / gx
+        tot = -0.5 * (mh.double().sum() + ld.double().sum())
+        if dist is not None:
+            dist.all_reduce(tot)
+        return tot
+
+    for _ in range(warmup):
+        step()
+    rk.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc_was = quiet_gc()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    rk.sync()
+    restore_gc(gc_was)
+    gr.check()
+    ms = rk.max_over_ranks(e0.elapsed_time(e1))
+    del gr
+    return ms
+
+
 def time_batch(rk, cr, tensors, steps, warmup):
     """K timed loglik+grad steps over this rank's series; returns (ms max over ranks, step fn, checksum, launches)."""
     from cyclic_gps import _native
@@ -747,12 +782,20 @@ def main():
         if world == 1:
             strong = {"series_total": B, "series_per_gpu": B, "ms_per_step": ms / args.steps, "value": value, "unit": UNIT,
                       "note": "one GPU: identical to the headline run"}
+            ms_g = time_graphed(rk, (R, O, x), args.steps, args.warmup)
+            if ms_g is not None:
+                strong["cuda_graph"] = {"ms_per_step": ms_g / args.steps, "value": B * n * args.steps / (ms_g * 1e-3), "unit": UNIT,
+                                        "what": "the same step as ONE CUDA-graph replay (cyclic_gps.graphs.GraphedMahalAndDet)"}
         elif B % world == 0:
             Bs = B // world
             sub_t = tuple(t.detach()[:Bs].requires_grad_(True) for t in (R, O, x))
             ms_s, _, _, _ = time_batch(rk, cr, sub_t, args.steps, args.warmup)
             strong = {"series_total": B, "series_per_gpu": Bs, "ms_per_step": ms_s / args.steps,
                       "value": B * n * args.steps / (ms_s * 1e-3), "unit": UNIT}
+            ms_g = time_graphed(rk, sub_t, args.steps, args.warmup)
+            if ms_g is not None:
+                strong["cuda_graph"] = {"ms_per_step": ms_g / args.steps, "value": B * n * args.steps / (ms_g * 1e-3), "unit": UNIT,
+                                        "what": "the same step as ONE CUDA-graph replay (cyclic_gps.graphs.GraphedMahalAndDet)"}
             del sub_t
 
     # ---- end to end: HOST buffers in (time stamps + observations), per-series scalars out, copies inside the timed region.
