@@ -1,3 +1,5 @@
+"""Packed lower triangles vs full blocks: prints the two bench lines and the per-level launch times written by
+`CRB200_TRI=1|0 python bench.py --no-long --no-strong --no-cpu-baseline --no-e2e --levels-out gpurun_out/s3_levels_tri$t.json > gpurun_out/s3_bench_tri$t.json`."""
 import json,sys
 for t in (1,0):
     d=json.loads(open(f"gpurun_out/s3_bench_tri{t}.json").read().strip().splitlines()[-1])
