@@ -561,6 +561,51 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
         main_s.synchronize()                              # the caller holds the result on the host
         return hout
 
+    # second pipeline: the batch is BUILT slice by slice (the builder of slice c runs while slice c + 1 crosses PCIe: builder and copy take
+    # about the same time) into one (B, n, l, l) pair of tensors, and ONE cyclic reduction runs over all series (a 128-series sweep costs
+    # 18 us per series, the full batch 8.6).  The blocks live in storage the caller owns (peg_precision(out=...)).
+    if B >= 64 and args.e2e_chunks > 1:
+        first2 = max(1, B // args.e2e_first_frac)
+        sizes2 = [first2] + [(B - first2) // 3 + (1 if i < (B - first2) % 3 else 0) for i in range(3)]
+    else:
+        sizes2 = [B]
+    bounds2 = [0]
+    for z in sizes2:
+        bounds2.append(bounds2[-1] + z)
+    R_all = torch.empty((B, n, ell, ell), dtype=dtype, device=dev)
+    O_all = torch.empty((B, n - 1, ell, ell), dtype=dtype, device=dev)
+
+    def e2e_step_build_stream():
+        main_s = torch.cuda.current_stream()
+        copy_stream.wait_stream(main_s)
+        ready = []
+        with torch.cuda.stream(copy_stream):
+            for c in range(len(sizes2)):
+                sl = slice(bounds2[c], bounds2[c + 1])
+                d_ts[sl].copy_(h_ts[sl], non_blocking=True)
+                d_xs[sl].copy_(h_xs[sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
+        with torch.no_grad():
+            for c in range(len(sizes2)):
+                sl = slice(bounds2[c], bounds2[c + 1])
+                main_s.wait_event(ready[c])
+                model._precision_blocks(d_ts[sl], shift, out=(R_all[sl], O_all[sl]))
+            v = model.compute_v(d_xs)
+        Rs, Os = R_all.detach().requires_grad_(True), O_all.detach().requires_grad_(True)
+        v.requires_grad_(True)
+        mm, dd = cr.mahal_and_det(Rs, Os, v)
+        ll = -0.5 * (mm.double().sum() + dd.double().sum())
+        ll.backward()
+        tot = ll.detach()
+        hout[0].copy_(mm.detach(), non_blocking=True)
+        hout[1].copy_(dd.detach(), non_blocking=True)
+        if dist is not None:
+            dist.all_reduce(tot)
+        main_s.synchronize()
+        return hout
+
     def timed(fn, k):
         fn(); fn()
         rk.sync()
@@ -576,13 +621,28 @@ def run_e2e(args, rk, cr, B, n, ell, dtype, R_dev, O_dev):
 
     k2 = max(3, min(args.steps, 5))
     ms2 = timed(e2e_step, k2)
+    ref_out = e2e_step().clone()
+    pipe = (f"chunks of {sizes} series, H2D on a copy stream under the compute of the previous chunk; "
+            "pinned host time stamps (fp64) + observations -> device; precision blocks built on the device "
+            "(crb200_peg_precision_fwd = the reference's compute_posterior_precision); cr.mahal_and_det + backward to gR, gO, gx; "
+            "per-series scalars -> host")
+    other = {"pipeline": "one cyclic reduction over the whole batch, blocks built slice by slice", "ms_per_step": None}
+    try:
+        ms2b = timed(e2e_step_build_stream, k2)
+        same = bool(torch.allclose(e2e_step_build_stream(), ref_out, rtol=1e-5, atol=1e-3))
+        other["ms_per_step"], other["same_scalars_as_the_chunked_pipeline"] = ms2b, same
+        if same and ms2b < ms2:
+            other = {"pipeline": "chunks of series, builder + cyclic reduction per chunk", "ms_per_step": ms2}
+            ms2 = ms2b
+            pipe = (f"slices of {sizes2} series cross PCIe on a copy stream while the precision builder (crb200_peg_precision_fwd = the reference's "
+                    "compute_posterior_precision, peg_precision(out=...)) fills the previous slice's blocks of ONE (B, n, l, l) batch; pinned host time "
+                    "stamps (fp64) + observations -> device; then ONE cr.mahal_and_det over all series + backward to gR, gO, gx; per-series scalars -> host")
+    except Exception as ex:  # noqa: BLE001
+        other["error"] = f"{type(ex).__name__}: {ex}"[:200]
+    del R_all, O_all
     h2d = h_ts.numel() * 8 + h_xs.numel() * s
     e2e = {"value": rows / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hout.numel() * s,
-           "ms_per_step": ms2, "steps": k2,
-           "pipeline": f"chunks of {sizes} series, H2D on a copy stream under the compute of the previous chunk; "
-                       "pinned host time stamps (fp64) + observations -> device; precision blocks built on the device "
-                       "(crb200_peg_precision_fwd = the reference's compute_posterior_precision); cr.mahal_and_det + backward to gR, gO, gx; "
-                       "per-series scalars -> host",
+           "ms_per_step": ms2, "steps": k2, "pipeline": pipe, "other_pipeline": other,
            "builder_vs_fp64_torch_blocks_rel": chk}
 
     # the whole training step of the reference (LEGFamily.log_likelihood: prior log-det + posterior mahal / log-det,

@@ -125,14 +125,14 @@ class LEGFamily(_Base):
             return t.device
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _precision_blocks(self, ts, shift=None, logdet=False):
+    def _precision_blocks(self, ts, shift=None, logdet=False, out=None):
         """(Rs, Os) on the compute device, built by ONE kernel from the time gaps (cyclic_gps.peg) with a
         hand-written backward to G and the diagonal shift.  ts (n,) or (B,n).  logdet=True: also log det of the unshifted
         (prior) precision, a by-product of the same kernel."""
         dev = self._compute_device(ts)
         t = ts.to(dev)
         gaps = (t[..., 1:] - t[..., :-1]).to(self.G.dtype)
-        return peg_precision(gaps, self.G, shift, logdet=logdet)
+        return peg_precision(gaps, self.G, shift, logdet=logdet, out=out)
 
     def compute_PEG_precision(self, ts):
         """Diagonal (n,l,l) and lower off-diagonal (n-1,l,l) blocks of the PEG precision, on the caller's device; a leading

@@ -160,12 +160,19 @@ class _EigConsts:
         return (self.Vinv.transpose(0, 1) @ Z @ self.V.transpose(0, 1)).real
 
 
-def builder_forward(c, gaps, shift64, dtype, want_logdet=True):
-    """One launch of crb200_peg_precision_fwd: gaps (B, n-1) -> R, O, log det of the unshifted precision (B,) float64, info."""
+def builder_forward(c, gaps, shift64, dtype, want_logdet=True, out=None):
+    """One launch of crb200_peg_precision_fwd: gaps (B, n-1) -> R, O, log det of the unshifted precision (B,) float64, info.
+    out = (R, O): write into these contiguous (B, n, l, l) / (B, n-1, l, l) tensors (e.g. a slice of series of a larger batch)."""
     B, nm1 = gaps.shape
     n, l, dev = nm1 + 1, c.V.shape[0], gaps.device
-    R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
-    O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
+    if out is not None:
+        R, O = out
+        if (tuple(R.shape) != (B, n, l, l) or tuple(O.shape) != (B, nm1, l, l) or R.dtype != dtype or O.dtype != dtype
+                or R.device != dev or O.device != dev or not R.is_contiguous() or not O.is_contiguous()):
+            raise ValueError("out = (R, O) must be contiguous (B, n, l, l) / (B, n-1, l, l) tensors of the dtype and device of the gaps")
+    else:
+        R = torch.empty((B, n, l, l), dtype=dtype, device=dev)
+        O = torch.empty((B, nm1, l, l), dtype=dtype, device=dev)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     ld = torch.zeros(B, dtype=torch.float64, device=dev)
     _native.peg_fwd(dtype, l, batch=B, n=n, gaps=gaps if nm1 > 0 else None, stride_gaps=gaps.stride(0) if nm1 > 0 else 0,
@@ -252,7 +259,7 @@ def device_builder_available(rank: int) -> bool:
     return torch.cuda.is_available() and rank <= _native.peg_max_ell()
 
 
-def peg_precision(gaps, G, shift=None, check=True, logdet=False):
+def peg_precision(gaps, G, shift=None, check=True, logdet=False, out=None):
     """gaps (B, n-1) or (n-1,) on a CUDA device (float32 / float64 = the dtype of the blocks), G (l,l) and shift (l,l)
     anywhere (they are tiny): returns (Rs, Os) on the device of `gaps`.  Differentiable wrt G and shift.
 
@@ -263,6 +270,21 @@ def peg_precision(gaps, G, shift=None, check=True, logdet=False):
     runs a second cyclic reduction (models.py:349-353); it is differentiable (its cotangent adds 2 g B_g to the cotangent of A_g)."""
     single = gaps.dim() == 1
     g2 = gaps.unsqueeze(0) if single else gaps
+    if out is not None:
+        # the blocks of a batch of series written into caller-owned storage (a pipeline that builds a large batch slice by slice
+        # while the next slice is still crossing PCIe); no autograd through this form
+        if single or torch.is_grad_enabled() and (G.requires_grad or (shift is not None and shift.requires_grad)):
+            raise ValueError("peg_precision(out=...) takes a batch of series and is not differentiable: call it under torch.no_grad()")
+        if not (g2.is_cuda and device_builder_available(G.shape[0])):
+            raise ValueError("peg_precision(out=...) needs the device builder")
+        consts = _consts_for(G, g2.device)
+        if consts.cond > EIG_COND_MAX or not consts.folded:
+            res = peg_precision_torch(g2, G.to(g2.device, g2.dtype), shift.to(g2.device, g2.dtype) if shift is not None else None, logdet=logdet)
+            out[0].copy_(res[0]); out[1].copy_(res[1])
+            return (out[0], out[1], res[2].to(torch.float64)) if logdet else (out[0], out[1])
+        sh = shift.detach().to(g2.device, torch.float64).contiguous() if shift is not None else None
+        R, O, ld, _ = builder_forward(consts, g2.contiguous(), sh, g2.dtype, logdet, out=out)
+        return (R, O, ld) if logdet else (R, O)
     use_torch = not (g2.is_cuda and device_builder_available(G.shape[0]))
     if not use_torch:
         consts = _consts_for(G, g2.device)
