@@ -151,3 +151,30 @@ def test_builder_many_tiles_per_persistent_cta(l, dtype, tol_f, tol_g):
     ((R1 * cR.to(dtype)).sum() + (O1 * cO.to(dtype)).sum() + (ld1 * cl).sum()).backward()
     assert_close(sd.grad, sr.grad, tol_g, "g shift")
     assert_close(Gd.grad, Gr.grad, tol_g, "gG")
+
+
+@pytest.mark.parametrize("l,dtype", [(8, torch.float32), (3, torch.float64), (16, torch.float64)])
+def test_builder_writes_into_caller_storage_slice_by_slice(l, dtype):
+    """peg_precision(out=(R, O)): a large batch built a slice of series at a time (bench.py's end-to-end pipeline builds the slice that has
+    crossed PCIe while the next one is in flight) equals the one-call result bit for bit; the form is not differentiable."""
+    from cyclic_gps.peg import peg_precision
+    G, shift = _model_G(l, seed=11)
+    B, n = 13, 141
+    gaps = (torch.rand((B, n - 1), generator=torch.Generator().manual_seed(5), dtype=torch.float64) + 0.02).to(dtype).cuda()
+    with torch.no_grad():
+        R1, O1, ld1 = peg_precision(gaps, G, shift, logdet=True)
+        R2 = torch.full((B, n, l, l), float("nan"), dtype=dtype, device="cuda")
+        O2 = torch.full((B, n - 1, l, l), float("nan"), dtype=dtype, device="cuda")
+        lds = []
+        for lo, hi in ((0, 4), (4, 5), (5, 13)):
+            r, o, ld = peg_precision(gaps[lo:hi], G, shift, logdet=True, out=(R2[lo:hi], O2[lo:hi]))
+            assert r.data_ptr() == R2[lo:hi].data_ptr() and o.data_ptr() == O2[lo:hi].data_ptr()
+            lds.append(ld)
+    assert torch.equal(R1, R2) and torch.equal(O1, O2)
+    assert_close(torch.cat(lds), ld1, 1e-12, "logdet of the slices")
+    Gg = G.clone().requires_grad_(True)
+    with pytest.raises(ValueError):
+        peg_precision(gaps[:2], Gg, shift, out=(R2[:2], O2[:2]))                      # differentiable inputs
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            peg_precision(gaps[:2], G, shift, out=(R2[:3], O2[:2]))                   # wrong shape
