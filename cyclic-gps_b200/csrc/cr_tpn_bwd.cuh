@@ -22,6 +22,9 @@
 // Small blocks keep FIVE blocks per node, [ A | SD | C | B | SO | X | WT ]: everything is requested up front,
 // Sigma_{2e,2e} is written into A, and (A, SD), (C, B), (X, WT) leave as interleaved pairs.
 // Record 0 is the left neighbour (deeper-level node e0-1) and only carries S~_d and WT.
+// Packed lower triangles (crb200_bwd_args.tri, TriPack in cr_tpn_common.cuh; COMPACT layout, float32 ell = 8): D and S~_d arrive as 36 elements at
+// the start of the A slot; S~_d is expanded to full symmetric rows in place once it has landed (the products read rows of it), and on inner
+// levels both halves of Sigma_d leave packed straight from registers (the odd rows at the expansion, the even rows at the end).
 #pragma once
 #include "cr_level_bwd.cuh"
 #include "cr_tpn_common.cuh"

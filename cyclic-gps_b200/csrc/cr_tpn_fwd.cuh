@@ -18,6 +18,8 @@
 // Three blocks per node instead of five means 8 resident CTAs per SM instead of 5; measured throughput of
 // this kernel scales almost linearly with resident CTAs (profiles/r1_summary.md).
 // The odd record stride makes the per-thread 16-byte accesses conflict free.
+// Packed lower triangles (crb200_fwd_args.tri, TriPack in cr_tpn_common.cuh; float32 ell = 8): R of the inner levels arrives as 36 elements at
+// the start of the R slot, K and R~ are written there packed and leave packed; everything else is unchanged.
 #pragma once
 #include "cr_common.cuh"
 #include "cr_level_fwd.cuh"
