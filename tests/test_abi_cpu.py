@@ -43,6 +43,46 @@ def test_argument_validation_without_gpu():
     assert lib.crb200_fwd_tile_nodes(0, 8) == 31 and lib.crb200_bwd_tile_nodes(0, 8) >= 1
 
 
+def test_packed_triangle_requests_are_validated_without_gpu():
+    """`tri` (packed lower triangles): offered for float32 ell = 8 only, never with a halo, a forced non-thread-per-node family,
+    a partial sweep or the gradient mode of an inner-level output; all of it is rejected before anything is launched."""
+    from cyclic_gps import _native
+    lib = _native.load()
+    assert lib.crb200_tri_stride(_native.F32, 8) == 36
+    assert all(lib.crb200_tri_stride(dt, l) == 0 for dt in (_native.F32, _native.F64) for l in range(1, 33) if (dt, l) != (_native.F32, 8))
+    assert lib.crb200_tri_stride(7, 8) == 0 and lib.crb200_tri_stride(_native.F32, 40) == 0
+    buf = ctypes.create_string_buffer(1 << 16)                      # host memory: only its (aligned) address is looked at
+    base = (ctypes.addressof(buf) + 255) & ~255
+    a = _native.FwdArgs()
+    a.batch, a.m = 1, 4
+    for f in ("R", "O", "D", "F", "G", "Rn", "On"):
+        setattr(a, f, base)
+    a.tri = 2
+    assert lib.crb200_level_fwd(_native.F32, 4, ctypes.byref(a), None) == _native.EINVAL        # size without packed storage
+    assert lib.crb200_level_fwd(_native.F64, 8, ctypes.byref(a), None) == _native.EINVAL
+    a.variant = 1                                                                                  # lane-per-row family forced
+    assert lib.crb200_level_fwd(_native.F32, 8, ctypes.byref(a), None) == _native.EINVAL
+    a.variant, a.tri = 0, 4                                                                        # unknown bit
+    assert lib.crb200_level_fwd(_native.F32, 8, ctypes.byref(a), None) == _native.EINVAL
+    a.tri, a.Rn = 2, base + 4                                                                      # packed output not 16-byte aligned
+    assert lib.crb200_level_fwd(_native.F32, 8, ctypes.byref(a), None) == _native.EINVAL
+    a.Rn = base
+    a.O_halo = a.Rh_acc = a.On_halo = a.G_halo = base                                              # chunked (halo) sweeps keep full blocks
+    assert lib.crb200_level_fwd(_native.F32, 8, ctypes.byref(a), None) == _native.EINVAL
+    b = _native.BwdArgs()
+    b.batch, b.m = 1, 4
+    for f in ("D", "F", "G", "Sd_in", "So_in", "Sd_out", "So_out"):
+        setattr(b, f, base)
+    b.tri, b.grad_mode = 3, 1                                                                      # level 0 writes the caller's full gradient
+    assert lib.crb200_level_bwd(_native.F32, 8, ctypes.byref(b), None) == _native.EINVAL
+    s = _native.SweepFwdArgs()
+    s.batch, s.n, s.nlevels, s.R, s.tri = 1, 100, 3, base, 1                                       # partial sweep: the rest system is handed out
+    assert lib.crb200_sweep_fwd(_native.F32, 8, ctypes.byref(s), None) == _native.EINVAL
+    t = _native.SweepBwdArgs()
+    t.batch, t.n, t.nlevels, t.D, t.tri, t.top_Sd = 1, 100, 7, base, 1, base                       # a seeded descent has full blocks on top
+    assert lib.crb200_sweep_bwd(_native.F32, 8, ctypes.byref(t), None) == _native.EINVAL
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
 def test_no_cpu_fallback():
     from cyclic_gps import cyclic_reduction as cr
