@@ -84,7 +84,7 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
 
   // ---------------- stage in, first group: factors D, F, G and the vectors ----------------
   {
-    if (tri_in) rec_g2s<T, PKS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * PKS, 0, nE, is_aligned16(a.D));
+    if (tri_in) rec_g2s<T, PKS, 1, true>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * PKS, 0, nE, is_aligned16(a.D));
     else rec_g2s<T, BS, 1>(rec1 + Cf::A * ES, nsb, static_cast<const T*>(a.D) + ((size_t)b * E + e0) * BS, 0, nE, is_aligned16(a.D));
     rec_g2s<T, BS, 1>(rec1 + Cf::B * ES, nsb, static_cast<const T*>(a.F) + ((size_t)b * o + e0) * BS, 0, nF, is_aligned16(a.F));
     const int gf = (e0 == 0) ? 1 : 0;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void tpn_bwd_tile(const LevelBwdArgs& a, unsigned cha
   auto stage_Sd = [&]() {
     if (do_sigma) {
       if (tri_in)
-        rec_g2s<T, PKS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * PKS, ilo, nodd,
+        rec_g2s<T, PKS, 1, true>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * PKS, ilo, nodd,
                            is_aligned16(a.Sd_in));
       else
         rec_g2s<T, BS, 1>(s0 + Cf::SD * ES, nsb, static_cast<const T*>(a.Sd_in) + ((size_t)b * o + (e0 - 1 + ilo)) * BS, ilo, nodd,

@@ -70,6 +70,9 @@ __device__ __forceinline__ int4 lds128_u32(unsigned saddr) {
 // Chunk walk for units of CPU 16-byte chunks when neither 32 % CPU nor CPU % 32 is zero (packed lower triangles: CPU = 9), one unit per
 // record: fully unrolled over the at most MAXU units of a tile, so that a chunk costs one compare + select for the record wrap and
 // immediates for everything else (the generic path divides per chunk).  f(saddr, j, wrap): lane's chunk number lane + 32 j.
+// Used only where a caller asks for it (template flag WALK of the rec_* functions: the packed-triangle fields).  Measured on B200: for the
+// 25-chunk blocks of float32 ell = 10 the unrolled walk cost registers that kernel does not have (14.9 -> 25.4 ms per step) and it is neutral for
+// the 9- and 18-chunk full blocks of ell = 6, so every other field keeps the generic loop.
 constexpr int kMaxTileUnits = 33;
 template <int CPU, int MAXU, typename F>
 __device__ __forceinline__ void chunk_walk(unsigned srec0, unsigned nsb, int kstart, int nunits, F f) {
@@ -92,7 +95,7 @@ __device__ __forceinline__ void chunk_walk(unsigned srec0, unsigned nsb, int kst
 // (GRP = 1: one unit per record; GRP = 2: units 2t, 2t+1 are adjacent fields of record t).
 // Unit index k = kstart + j goes to record k / GRP, sub-field k % GRP.
 // `srec0` = shared address of the field in record 0, `nsb` = record stride in bytes.
-template <typename T, int UE, int GRP>
+template <typename T, int UE, int GRP, bool WALK = false>
 __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* __restrict__ g, int kstart, int nunits, bool vec_ok) {
   constexpr int VE = 16 / (int)sizeof(T);
   if (nunits <= 0) return;
@@ -123,7 +126,7 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
         }
         return;
       }
-      if constexpr (GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
+      if constexpr (WALK && GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
         chunk_walk<CPR, kMaxTileUnits>(srec0, nsb, kstart, nunits, [&](unsigned saddr, int j, bool) { cp_async16_u32(saddr, gp + 512 * j); });
         return;
       }
@@ -144,7 +147,7 @@ __device__ __forceinline__ void rec_g2s(unsigned srec0, unsigned nsb, const T* _
 
 // Every GS-th global unit -> one unit per record (unit j = global unit j * GS lands in record kstart + j).
 // Used to stage only the even (or only the odd) rows of a level.
-template <typename T, int UE, int GS>
+template <typename T, int UE, int GS, bool WALK = false>
 __device__ __forceinline__ void rec_g2s_strided(unsigned srec0, unsigned nsb, const T* __restrict__ g, int kstart, int nunits, bool vec_ok) {
   constexpr int VE = 16 / (int)sizeof(T);
   if (nunits <= 0) return;
@@ -162,7 +165,7 @@ __device__ __forceinline__ void rec_g2s_strided(unsigned srec0, unsigned nsb, co
         for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) cp_async16_u32(saddr, gp);
         return;
       }
-      if constexpr (CPU < 32) if (nunits <= kMaxTileUnits) {
+      if constexpr (WALK && CPU < 32) if (nunits <= kMaxTileUnits) {
         // unit u = q0 + a + wrap, chunk c = c0 + b - CPU * wrap: the global side skips (GS - 1) units at every wrap
         const unsigned q0 = (unsigned)lane / CPU, c0 = (unsigned)lane - q0 * CPU;
         const char* g0 = reinterpret_cast<const char*>(g) + ((size_t)q0 * GS * CPU + c0) * 16;
@@ -220,7 +223,7 @@ __device__ __forceinline__ void stg_row(T* p, const T (&a)[L], bool vec_ok) {
 }
 
 // Records -> global units, same addressing.
-template <typename T, int UE, int GRP>
+template <typename T, int UE, int GRP, bool WALK = false>
 __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsigned nsb, int kstart, int nunits, bool vec_ok) {
   constexpr int VE = 16 / (int)sizeof(T);
   if (nunits <= 0) return;
@@ -248,7 +251,7 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
         }
         return;
       }
-      if constexpr (GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
+      if constexpr (WALK && GRP == 1 && CPR < 32) if (nunits <= kMaxTileUnits) {
         chunk_walk<CPR, kMaxTileUnits>(srec0, nsb, kstart, nunits, [&](unsigned saddr, int j, bool) { *reinterpret_cast<int4*>(gp + 512 * j) = lds128_u32(saddr); });
         return;
       }
@@ -269,7 +272,7 @@ __device__ __forceinline__ void rec_s2g(T* __restrict__ g, unsigned srec0, unsig
 
 // One unit per record -> every GS-th global unit (record kstart + j -> global unit j * GS): the mirror of
 // rec_g2s_strided, used to write only the odd rows of an interleaved output.
-template <typename T, int UE, int GS>
+template <typename T, int UE, int GS, bool WALK = false>
 __device__ __forceinline__ void rec_s2g_strided(T* __restrict__ g, unsigned srec0, unsigned nsb, int kstart, int nunits, bool vec_ok) {
   constexpr int VE = 16 / (int)sizeof(T);
   if (nunits <= 0) return;
@@ -287,7 +290,7 @@ __device__ __forceinline__ void rec_s2g_strided(T* __restrict__ g, unsigned srec
         for (int i = lane; i < total; i += 32, gp += gstep, saddr += sstep) *reinterpret_cast<int4*>(gp) = lds128_u32(saddr);
         return;
       }
-      if constexpr (CPU < 32) if (nunits <= kMaxTileUnits) {
+      if constexpr (WALK && CPU < 32) if (nunits <= kMaxTileUnits) {
         const unsigned q0 = (unsigned)lane / CPU, c0 = (unsigned)lane - q0 * CPU;
         char* g0 = reinterpret_cast<char*>(g) + ((size_t)q0 * GS * CPU + c0) * 16;
         char* g1 = g0 + (size_t)(GS - 1) * CPU * 16;

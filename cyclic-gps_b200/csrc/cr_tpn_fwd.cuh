@@ -76,7 +76,7 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
-    if (tri_in) rec_g2s_strided<T, PKS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * PKS, 0, (nR + 1) >> 1, is_aligned16(gR));
+    if (tri_in) rec_g2s_strided<T, PKS, 2, true>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * PKS, 0, (nR + 1) >> 1, is_aligned16(gR));
     else rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)r0 * BS, 0, (nR + 1) >> 1, is_aligned16(gR));   // even rows
     if (has_y) rec_g2s<T, L, 2>(s0 + C::YE * ES, nsb, gy + (size_t)r0 * L, 0, nR, is_aligned16(gy));
     cp_async_commit();
@@ -93,7 +93,7 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   const int n_odd = cmax(0, cmin(OWN, o - e0));
   auto out_D_x = [&]() {
     if (a.D != nullptr) {
-      if (tri_out) rec_s2g<T, PKS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
+      if (tri_out) rec_s2g<T, PKS, 1, true>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
       else rec_s2g<T, BS, 1>(static_cast<T*>(a.D) + ((size_t)b * E + e0) * BS, s0 + C::RE * ES, nsb, 0, n_own, is_aligned16(a.D));
     }
     if (a.xk != nullptr && has_y)
@@ -114,7 +114,7 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   };
   auto out_reduced = [&]() {
     if (a.Rn != nullptr && n_odd > 0) {
-      if (tri_out) rec_s2g<T, PKS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
+      if (tri_out) rec_s2g<T, PKS, 1, true>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * PKS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
       else rec_s2g<T, BS, 1>(static_cast<T*>(a.Rn) + ((size_t)b * o + e0) * BS, s0 + C::RE * ES, nsb, 0, n_odd, is_aligned16(a.Rn));
       if (has_y && a.yn != nullptr)
         rec_s2g<T, L, 1>(static_cast<T*>(a.yn) + ((size_t)b * o + e0) * L, s0 + C::YO * ES, nsb, 0, n_odd, is_aligned16(a.yn));
@@ -124,7 +124,7 @@ __device__ __forceinline__ void tpn_fwd_tile(const LevelFwdArgs& a, unsigned cha
   auto stage_R_odd = [&]() {
     const int r0 = 2 * e0;
     const int nR = cmin(2 * NT - 1, m - r0);
-    if (tri_in) rec_g2s_strided<T, PKS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * PKS, 0, nR >> 1, is_aligned16(gR));
+    if (tri_in) rec_g2s_strided<T, PKS, 2, true>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * PKS, 0, nR >> 1, is_aligned16(gR));
     else rec_g2s_strided<T, BS, 2>(s0 + C::RE * ES, nsb, gR + (size_t)(r0 + 1) * BS, 0, nR >> 1, is_aligned16(gR));
     cp_async_commit();
   };
